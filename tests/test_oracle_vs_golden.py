@@ -1,0 +1,118 @@
+"""Pin the CPU oracle (oracle/) against golden vectors produced by the reference itself.
+
+The fixtures in tests/golden/ were written by oracle/make_golden.py, which imports the
+reference (`dataloader/encodings.py`, `models/*.py`) in the build container.  CPU only.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import bmcnet_fp32 as M
+from oracle import encodings_np as E
+
+
+def _enc_cases(golden_dir):
+    return sorted(glob.glob(os.path.join(golden_dir, 'enc_*.npz')))
+
+
+ENC_FNS = {
+    'image': lambda a, h, w, B: E.events_to_image(a[0], a[1], a[3], sensor_size=(h, w)),
+    'channels': lambda a, h, w, B: E.events_to_channels(a[0], a[1], a[3], sensor_size=(h, w)),
+    'voxel': lambda a, h, w, B: E.events_to_voxel(a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'image_torch': lambda a, h, w, B: E.events_to_image_torch(a[0], a[1], a[3], sensor_size=(h, w)),
+    'image_torch_bilinear': lambda a, h, w, B: E.events_to_image_torch(
+        a[0], a[1], a[3], sensor_size=(h, w), interpolation='bilinear'),
+    'stack_polarity': lambda a, h, w, B: E.events_to_stack_polarity(
+        a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'stack_no_polarity': lambda a, h, w, B: E.events_to_stack_no_polarity(
+        a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'voxel_torch': lambda a, h, w, B: E.events_to_voxel_torch(
+        a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'voxel_torch_hard': lambda a, h, w, B: E.events_to_voxel_torch(
+        a[0], a[1], a[2], a[3], B, sensor_size=(h, w), temporal_bilinear=False),
+}
+
+
+@pytest.mark.parametrize('fname', sorted(ENC_FNS))
+def test_encoder_oracle_bit_exact_vs_reference_goldens(golden_dir, fname):
+    cases = _enc_cases(golden_dir)
+    assert len(cases) >= 8
+    for path in cases:
+        g = np.load(path)
+        h, w, B = int(g['h']), int(g['w']), int(g['B'])
+        args = [g['in_' + k].copy() for k in ('xs', 'ys', 'ts', 'ps')]
+        out = ENC_FNS[fname](args, h, w, B)
+        ref = g['out_' + fname]
+        assert out.shape == ref.shape, (path, fname)
+        # the oracle keeps the reference's serial fp32 order, so even weighted sums are bit-exact
+        assert np.array_equal(out, ref), (path, fname, float(np.abs(out - ref).max()))
+        for i, k in enumerate(('xs', 'ys', 'ts', 'ps')):          # in-place side effects (F9)
+            key = 'mut_%s_%s' % (fname, k)
+            want = g[key] if key in g.files else g['in_' + k]
+            assert np.array_equal(args[i], want), (path, fname, k)
+
+
+def test_binary_search_returns_any_equal_index():
+    # the search probes l, r, mid each round and returns the first hit
+    t = np.array([0.0, 0.1, 0.1, 0.1, 0.1, 0.5, 0.9], dtype=np.float32)
+    assert E.binary_search_torch_tensor(t, 0, len(t) - 1, np.float32(0.1)) == 3
+    assert E.binary_search_torch_tensor(t, 0, len(t) - 1, np.float32(0.3)) == 5
+    assert E.binary_search_torch_tensor(t, 0, len(t) - 1, np.float32(0.3), side='right') == 4
+    assert E.binary_search_torch_tensor(t, 0, len(t) - 1, np.float32(2.0), side='right') == 6
+    assert E.binary_search_torch_tensor(t, 0, len(t) - 1, np.float32(-1.0), side='right') == -1
+
+
+def _rollout(fwd, sd, g, n_state):
+    x = torch.from_numpy(g['x'])
+    b, h, w = x.shape[1], x.shape[-2], x.shape[-1]
+    st = [torch.zeros(b, 128, h, w) for _ in range(n_state - 1)] + [torch.zeros(b, 32, h, w)]
+    outs = []
+    init = True
+    for s in range(x.shape[0]):
+        st = list(fwd(sd, x[s], *st, init))
+        init = False
+        outs.append(st[-1])
+    return torch.stack(outs), st[:-1]
+
+
+def test_plain_oracle_vs_reference_shipped_checkpoint(golden_dir, plain_ckpt):
+    g = np.load(os.path.join(golden_dir, 'model_plain_shipped.npz'))
+    outs, hid = _rollout(M.bmcnet_plain_forward, plain_ckpt, g, 2)
+    assert torch.allclose(outs, torch.from_numpy(g['x_o']), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(hid[0], torch.from_numpy(g['x_h']), atol=1e-5, rtol=1e-5)
+
+
+def test_plain_oracle_vs_reference_surrogate(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'model_plain_surrogate.npz'))
+    sd = M.surrogate_state_dict(plain=True, seed=int(g['seed']))
+    outs, hid = _rollout(M.bmcnet_plain_forward, sd, g, 2)
+    assert torch.allclose(outs, torch.from_numpy(g['x_o']), atol=1e-5, rtol=1e-5)
+    assert torch.allclose(hid[0], torch.from_numpy(g['x_h']), atol=1e-5, rtol=1e-5)
+
+
+@pytest.mark.parametrize('tag', ['surrogate', 'transplant'])
+def test_bmcnet_oracle_vs_reference(golden_dir, tag, request):
+    g = np.load(os.path.join(golden_dir, 'model_bmcnet_%s.npz' % tag))
+    tr = request.getfixturevalue('plain_ckpt') if tag == 'transplant' else None
+    sd = M.surrogate_state_dict(plain=False, seed=int(g['seed']), transplant=tr)
+    outs, hid = _rollout(M.bmcnet_forward, sd, g, 4)
+    assert torch.allclose(outs, torch.from_numpy(g['x_o']), atol=1e-5, rtol=1e-5)
+    for t, k in zip(hid, ('x_h', 'x_h_p', 'x_h_n')):
+        assert torch.allclose(t, torch.from_numpy(g[k]), atol=1e-5, rtol=1e-5), k
+
+
+@pytest.mark.parametrize('plain', [False, True])
+def test_state_dict_contract(golden_dir, plain):
+    g = np.load(os.path.join(golden_dir, 'statedict_%s.npz' % ('plain' if plain else 'bmcnet')))
+    keys = M.bmcnet_state_dict_keys(5, plain)
+    assert keys == [str(k) for k in g['keys']]
+    assert len(keys) == (120 if plain else 318)
+    sd = M.surrogate_state_dict(plain=plain)
+    assert [str(tuple(sd[k].shape)) for k in keys] == [str(s) for s in g['shapes']]
+    ptr = {}
+    groups = [ptr.setdefault(sd[k].data_ptr(), len(ptr)) for k in keys]
+    assert groups == [int(v) for v in g['alias_group']]
+    assert sum(sd[r].numel() for r in {M._alias_root(k) for k in keys}) == int(g['n_unique_params'])
