@@ -1,0 +1,488 @@
+// Event encoders for sm_100a: (x, y, t, p) event streams -> count / image / voxel / stack grids.
+//
+// Reference semantics: dataloader/encodings.py:6-305 (see include/bmc_b200.h for the per-entry
+// mapping).  The work is an HBM-bound histogram: 12 B/event (xs, ys, ps) for counts and stacks,
+// 16 B/event (+ts) for voxels, read once with 128-bit streaming loads by a persistent grid
+// (a multiple of the SM count); each CTA privatises the whole output grid in shared memory
+// (int32 bins, or 16-bit packed bins with exact carry handling when the grid only fits that
+// way in the 227 KB of a B200 SM), and flushes its non-zero bins to a global int32/fp32 grid
+// with one atomic per bin.  Integer counting makes the result independent of event order, i.e.
+// bit-exact against the reference's serial fp32 accumulation (which saturates at 2^24; the
+// finalize step reproduces that).
+#include "common.cuh"
+
+namespace bmc {
+namespace {
+
+constexpr int kThreads = 512;
+constexpr int kSmemBudget = 227 * 1024;        // dynamic smem per CTA on sm_100
+constexpr int kMaxBinsSmem32 = 49152;          // 192 KB of int32 / fp32 bins
+constexpr int kMaxBinsSmem16 = kSmemBudget / 2;  // 16-bit packed bins
+
+enum Mode { kSmem32 = 0, kSmem16 = 1, kGlobal = 2 };
+
+__device__ __forceinline__ float4 ldg_stream4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+// Decoded spatial part of one event (encodings.py:249-265 / :34-39,67-70).
+struct Pix {
+    bool oor;
+    int x, y;   // truncated toward zero like `.long()`, y already flipped if requested
+};
+__device__ __forceinline__ Pix decode_xy(float x, float y, int H, int W, bool flip) {
+    Pix p;
+    // NaN coordinates make every comparison false in the reference and then index with
+    // garbage; here they are treated as out of range.
+    p.oor = !((x < (float)W) & (x >= 0.f) & (y < (float)H) & (y >= 0.f));
+    p.x = p.oor ? 0 : (int)x;
+    int yy = p.oor ? 0 : (int)y;
+    p.y = flip ? (H - 1 - yy) : yy;
+    return p;
+}
+
+// ---------------------------------------------------------------- accumulation targets
+template <int MODE, bool FLOAT_HIST>
+struct Hist {
+    int* s_i;        // smem int32 bins / packed 16-bit pairs
+    float* s_f;      // smem fp32 bins (FLOAT_HIST)
+    int* g_cnt;      // global int32 grid
+    float* g_ext;    // global fp32 grid (non-integral weights)
+
+    __device__ __forceinline__ void add_int(int bin, int delta) {
+        if (MODE == kSmem32) {
+            atomicAdd(&s_i[bin], delta);
+        } else if (MODE == kSmem16) {
+            // Two 16-bit counters per word.  The one thread that moves a field from 0x7FFF to
+            // 0x8000 takes 0x8000 back out and credits it to the global grid; until that lands
+            // the field can only grow by the <= kThreads adds in flight, so it never reaches
+            // 0xFFFF and never carries into its neighbour: exact for any event distribution.
+            const int sh = (bin & 1) * 16;
+            unsigned old = atomicAdd(reinterpret_cast<unsigned*>(&s_i[bin >> 1]), 1u << sh);
+            if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {
+                atomicSub(reinterpret_cast<unsigned*>(&s_i[bin >> 1]), 0x8000u << sh);
+                atomicAdd(&g_cnt[bin], 32768);
+            }
+        } else {
+            atomicAdd(&g_cnt[bin], delta);
+        }
+    }
+    __device__ __forceinline__ void add_float(int bin, float w) {
+        if (FLOAT_HIST && MODE == kSmem32) atomicAdd(&s_f[bin], w);
+        else atomicAdd(&g_ext[bin], w);
+    }
+    // integral +-1 weights go to the exact integer path, everything else to fp32
+    __device__ __forceinline__ void add_weight(int bin, float w) {
+        if (FLOAT_HIST) { if (w != 0.f) add_float(bin, w); return; }
+        if (w == 1.f) add_int(bin, 1);
+        else if (w == -1.f && MODE != kSmem16) add_int(bin, -1);
+        else if (w != 0.f) atomicAdd(&g_ext[bin], w);
+    }
+};
+
+// ---------------------------------------------------------------- per-encoder event ops
+struct Common {
+    float* xs; float* ys; const float* ts; float* ps;
+    int H, W, bins;
+    unsigned flags;
+    __device__ __forceinline__ bool flip() const { return flags & BMC_ENC_FLIP_Y; }
+    __device__ __forceinline__ bool mutate() const { return flags & BMC_ENC_MUTATE; }
+    __device__ __forceinline__ bool quirks() const { return !(flags & BMC_ENC_NO_QUIRKS); }
+    __device__ __forceinline__ int origin() const { return flip() ? (H - 1) * W : 0; }
+    __device__ __forceinline__ void prepare(long) {}
+};
+
+// events_to_channels (encodings.py:290-305)
+struct ChannelsOp : Common {
+    static constexpr bool kBounds = false;
+    static constexpr bool kFloat = false, kNeedT = false, kSigned = false;
+    template <class HT>
+    __device__ __forceinline__ void run(HT& h, long i, float x, float y, float, float p) const {
+        Pix q = decode_xy(x, y, H, W, true);
+        const float w = p * p;              // ps * mask_{pos,neg} == ps^2 on the matching sign
+        if (!q.oor) {
+            const int bin = (p < 0.f ? H * W : 0) + q.y * W + q.x;
+            h.add_weight(bin, w);
+        } else {
+            // F9: after the positive pass zeroed xs/ys, the negative pass sees (0,0) in range
+            if (quirks() && p < 0.f) h.add_weight(H * W + (H - 1) * W, w);
+            if (mutate()) { xs[i] = 0.f; ys[i] = 0.f; }
+        }
+    }
+};
+
+// events_to_image (encodings.py:241-269) / events_to_image_torch (encodings.py:16-72)
+struct ImageOp : Common {
+    static constexpr bool kBounds = false;
+    static constexpr bool kFloat = true, kNeedT = false, kSigned = true;
+    template <class HT>
+    __device__ __forceinline__ void run(HT& h, long i, float x, float y, float, float p) const {
+        Pix q = decode_xy(x, y, H, W, flip());
+        if (q.oor) {
+            if (mutate()) { xs[i] = 0.f; ys[i] = 0.f; ps[i] = 0.f; }
+            return;
+        }
+        if (flags & BMC_ENC_BILINEAR) {     // padded (H+1)x(W+1) splat, encodings.py:57-65, 6-13
+            const float fx = floorf(x), fy = floorf(y);
+            const float dx = x - fx, dy = y - fy;
+            const int Wp = W + 1, base = (int)fy * Wp + (int)fx;
+            const float w0 = __fmul_rn(p, 1.f - dx), w1 = __fmul_rn(p, dx);
+            h.add_float(base, __fmul_rn(w0, 1.f - dy));
+            h.add_float(base + 1, __fmul_rn(w1, 1.f - dy));
+            h.add_float(base + Wp, __fmul_rn(w0, dy));
+            h.add_float(base + Wp + 1, __fmul_rn(w1, dy));
+        } else {
+            h.add_float(q.y * W + q.x, p);
+        }
+    }
+};
+
+// events_to_voxel (encodings.py:272-287) / events_to_voxel_torch bilinear (encodings.py:127-137)
+struct VoxelOp : Common {
+    static constexpr bool kBounds = false;
+    static constexpr bool kFloat = true, kNeedT = true, kSigned = true;
+    float t0, dt;     // only for BMC_ENC_TNORM
+    __device__ __forceinline__ void prepare(long n) {
+        if ((flags & BMC_ENC_TNORM) && n > 0) {      // dt = ts[-1]-ts[0] + 1e-6 (encodings.py:127)
+            t0 = ts[0];
+            dt = __fadd_rn(__fsub_rn(ts[n - 1], t0), 1e-6f);
+        }
+    }
+    template <class HT>
+    __device__ __forceinline__ void run(HT& h, long i, float x, float y, float t, float p) const {
+        Pix q = decode_xy(x, y, H, W, flip());
+        const float fb = (float)(bins - 1);
+        float tn;
+        if (flags & BMC_ENC_TNORM) tn = __fmul_rn(__fdiv_rn(__fsub_rn(t, t0), dt), fb);
+        else tn = __fmul_rn(t, fb);
+        if (q.oor && mutate()) { xs[i] = 0.f; ys[i] = 0.f; }
+        const int pix = q.oor ? origin() : q.y * W + q.x;
+        const int b0 = (int)floorf(tn);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int b = b0 + k;
+            if (b < 0 || b >= bins) continue;
+            // bin 0 is the pass that zeroes out-of-range events; later bins see them at (0,0)
+            if (q.oor && (b == 0 || !quirks())) continue;
+            const float w = fmaxf(0.f, __fsub_rn(1.f, fabsf(__fsub_rn(tn, (float)b))));
+            h.add_float(b * H * W + pix, __fmul_rn(p, w));
+        }
+    }
+};
+
+// events_to_stack_polarity / _no_polarity / voxel_torch(temporal_bilinear=False)
+// (encodings.py:151-238, 138-145): event i belongs to every bin b with beg[b] <= i < end[b].
+struct StackOp : Common {
+    static constexpr bool kFloat = false, kNeedT = false, kSigned = true, kBounds = true;
+    const long* beg; const long* end;    // device [bins]; re-pointed at a smem copy by the kernel
+    int polarity;
+    template <class HT>
+    __device__ __forceinline__ void run(HT& h, long i, float x, float y, float, float p) const {
+        Pix q = decode_xy(x, y, H, W, false);
+        bool first = true;
+        for (int b = 0; b < bins; ++b) {
+            if (i < beg[b] || i >= end[b]) continue;
+            const int plane = H * W;
+            if (polarity) {
+                const int base = (p < 0.f ? bins * plane : 0) + b * plane;
+                const float w = p * p;
+                if (!q.oor) h.add_weight(base + q.y * W + q.x, w);
+                else if (quirks() && (!first || p < 0.f)) h.add_weight(base, w);   // pixel (0,0)
+            } else {
+                if (!q.oor) h.add_weight(b * plane + q.y * W + q.x, p);
+            }
+            first = false;
+        }
+        if (q.oor && !first && mutate()) {
+            xs[i] = 0.f; ys[i] = 0.f;
+            if (!polarity) ps[i] = 0.f;       // the slice of ps is a view there (encodings.py:230-231)
+        }
+    }
+};
+
+// ---------------------------------------------------------------- the streaming kernel
+template <class Op, int MODE>
+__global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nbins, int* g_cnt,
+                                                           float* g_ext, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Hist<MODE, Op::kFloat> h;
+    h.s_i = reinterpret_cast<int*>(smem_raw);
+    h.s_f = reinterpret_cast<float*>(smem_raw);
+    h.g_cnt = g_cnt;
+    h.g_ext = g_ext;
+    const int words = (MODE == kSmem32) ? nbins : (MODE == kSmem16 ? (nbins + 1) / 2 : 0);
+    for (int k = threadIdx.x; k < words; k += kThreads) h.s_i[k] = 0;
+    if constexpr (Op::kBounds) {                 // bin ranges: 2*bins longs, read once per CTA
+        __shared__ long s_bounds[128];
+        if (threadIdx.x < op.bins) {
+            s_bounds[threadIdx.x] = op.beg[threadIdx.x];
+            s_bounds[64 + threadIdx.x] = op.end[threadIdx.x];
+        }
+        op.beg = s_bounds;
+        op.end = s_bounds + 64;
+    }
+    op.prepare(n);
+    __syncthreads();
+
+    const long n4 = vec_ok ? (n >> 2) : 0;
+    const long stride = (long)gridDim.x * kThreads;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < n4; g += stride) {
+        const long i = g << 2;
+        const float4 x = ldg_stream4(op.xs + i);
+        const float4 y = ldg_stream4(op.ys + i);
+        const float4 p = ldg_stream4(op.ps + i);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (Op::kNeedT) t = ldg_stream4(op.ts + i);
+        op.run(h, i + 0, x.x, y.x, t.x, p.x);
+        op.run(h, i + 1, x.y, y.y, t.y, p.y);
+        op.run(h, i + 2, x.z, y.z, t.z, p.z);
+        op.run(h, i + 3, x.w, y.w, t.w, p.w);
+    }
+    for (long i = (n4 << 2) + (long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+        op.run(h, i, op.xs[i], op.ys[i], Op::kNeedT ? op.ts[i] : 0.f, op.ps[i]);
+
+    if (MODE == kGlobal) return;
+    __syncthreads();
+    if (MODE == kSmem32) {
+        for (int k = threadIdx.x; k < nbins; k += kThreads) {
+            if (Op::kFloat) { const float v = h.s_f[k]; if (v != 0.f) atomicAdd(&g_ext[k], v); }
+            else { const int v = h.s_i[k]; if (v != 0) atomicAdd(&g_cnt[k], v); }
+        }
+    } else {
+        for (int k = threadIdx.x; k < words; k += kThreads) {
+            const unsigned v = (unsigned)h.s_i[k];
+            if (v & 0xFFFFu) atomicAdd(&g_cnt[2 * k], (int)(v & 0xFFFFu));
+            if (v >> 16) atomicAdd(&g_cnt[2 * k + 1], (int)(v >> 16));
+        }
+    }
+}
+
+// out = fp32(saturated count) + fp32 extras; the reference's serial `+= 1.0f` sticks at 2^24.
+__global__ void finalize_kernel(const int* __restrict__ cnt, const float* __restrict__ ext,
+                                float* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cnt[i];
+    c = max(-(1 << 24), min(c, 1 << 24));
+    out[i] = (float)c + ext[i];
+}
+
+// Bin boundaries of the stack encoders, evaluated exactly like encodings.py:172-178 + :75-97
+// (float32, two roundings for ts[0] + delta_t*bi, any-equal binary search).  One thread per
+// (bin, side); ~3 log2(n) dependent loads each.
+__global__ void bin_bounds_kernel(const float* __restrict__ ts, long n, int bins, long* beg,
+                                  long* end) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * bins) return;
+    const int bi = k >> 1;
+    const bool right = k & 1;
+    const float t0 = ts[0];
+    const float dt = __fadd_rn(__fsub_rn(ts[n - 1], t0), 1e-6f);
+    const float delta = __fdiv_rn(dt, (float)bins);
+    const float tstart = __fadd_rn(t0, __fmul_rn(delta, (float)bi));
+    const float x = right ? __fadd_rn(tstart, delta) : tstart;
+    long l = 0, r = n - 1, res = 0;
+    bool found = false;
+    while (l <= r) {
+        if (ts[l] == x) { res = l; found = true; break; }
+        if (ts[r] == x) { res = r; found = true; break; }
+        const long mid = l + (r - l) / 2;
+        const float mv = ts[mid];
+        if (mv == x) { res = mid; found = true; break; }
+        if (mv < x) l = mid + 1; else r = mid - 1;
+    }
+    if (!found) res = right ? r : l;
+    if (right) end[bi] = res + 1; else beg[bi] = res;
+}
+
+// One CTA per window (dataloader pattern: ~2048 events -> one [2,H,W] grid).  fp32 smem bins:
+// sums of +1.0f below 2^24 are exact integers in any order, so this is bit-exact too.
+__global__ void __launch_bounds__(256) channels_windows_kernel(
+    float* xs, float* ys, const float* ps, const long* __restrict__ offsets, int H, int W,
+    float* __restrict__ out, unsigned flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s = reinterpret_cast<float*>(smem_raw);
+    const int nb = 2 * H * W;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s[k] = 0.f;
+    __syncthreads();
+    const long b = offsets[blockIdx.x], e = offsets[blockIdx.x + 1];
+    const bool quirks = !(flags & BMC_ENC_NO_QUIRKS), mut = flags & BMC_ENC_MUTATE;
+    for (long i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const float x = xs[i], y = ys[i], p = ps[i];
+        Pix q = decode_xy(x, y, H, W, true);
+        const float w = p * p;
+        if (!q.oor) {
+            if (w != 0.f) atomicAdd(&s[(p < 0.f ? H * W : 0) + q.y * W + q.x], w);
+        } else {
+            if (quirks && p < 0.f) atomicAdd(&s[H * W + (H - 1) * W], w);
+            if (mut) { xs[i] = 0.f; ys[i] = 0.f; }
+        }
+    }
+    __syncthreads();
+    float* o = out + (long)blockIdx.x * nb;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) o[k] = s[k];
+}
+
+// ---------------------------------------------------------------- host-side launch logic
+struct Ws {
+    int* cnt; float* ext; long* beg; long* end;
+};
+
+size_t ws_bytes(long out_elems) { return (size_t)out_elems * 8 + 2 * 64 * sizeof(long) + 256; }
+
+int carve(void* ws, size_t ws_bytes_given, long out_elems, Ws& w) {
+    if (!ws || ws_bytes_given < ws_bytes(out_elems)) {
+        set_error("encoder workspace too small: need %zu bytes, got %zu", ws_bytes(out_elems),
+                  ws_bytes_given);
+        return BMC_ERR_WORKSPACE;
+    }
+    if ((uintptr_t)ws & 15) { set_error("encoder workspace must be 16-byte aligned"); return BMC_ERR_ARG; }
+    char* p = static_cast<char*>(ws);
+    w.cnt = reinterpret_cast<int*>(p);
+    w.ext = reinterpret_cast<float*>(p + (size_t)out_elems * 4);
+    size_t off = ((size_t)out_elems * 8 + 15) & ~(size_t)15;
+    w.beg = reinterpret_cast<long*>(p + off);
+    w.end = w.beg + 64;
+    return BMC_OK;
+}
+
+template <class Op, int MODE>
+int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaStream_t st) {
+    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : 0);
+    auto kern = scatter_kernel<Op, MODE>;
+    if (smem > 48 * 1024)
+        BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    BMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 4) per_sm = 4;
+    // Persistent grid: a multiple of the SM count, but never so many CTAs that flushing
+    // `nbins` bins per CTA outweighs the events each CTA streams.
+    long want = (n + (long)kThreads * 4 * 8 - 1) / ((long)kThreads * 4 * 8);
+    if (MODE != kGlobal) {
+        long by_flush = n / (4L * nbins) + 1;
+        if (want > by_flush) want = by_flush;
+    }
+    long grid = (long)sm_count() * per_sm;
+    if (want < grid) grid = want < 1 ? 1 : want;
+    kern<<<(unsigned)grid, kThreads, smem, st>>>(op, n, nbins, w.cnt, w.ext, vec_ok);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+template <class Op>
+int run_scatter(const Op& op, long n, long out_elems, float* out, void* ws, size_t wsb,
+                cudaStream_t st) {
+    Ws w;
+    int rc = carve(ws, wsb, out_elems, w);
+    if (rc) return rc;
+    BMC_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)out_elems * 8, st));
+    if (n > 0) {
+        const int vec_ok = (((uintptr_t)op.xs | (uintptr_t)op.ys | (uintptr_t)op.ps |
+                             (uintptr_t)(Op::kNeedT ? op.ts : nullptr)) & 15) == 0;
+        const int nbins = (int)out_elems;
+        if (out_elems <= kMaxBinsSmem32) rc = launch_mode<Op, kSmem32>(op, n, nbins, w, vec_ok, st);
+        else if (!Op::kFloat && !Op::kSigned && out_elems <= kMaxBinsSmem16)
+            rc = launch_mode<Op, kSmem16>(op, n, nbins, w, vec_ok, st);
+        else rc = launch_mode<Op, kGlobal>(op, n, nbins, w, vec_ok, st);
+        if (rc) return rc;
+    }
+    const int thr = 256;
+    finalize_kernel<<<(unsigned)((out_elems + thr - 1) / thr), thr, 0, st>>>(w.cnt, w.ext, out, out_elems);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int check_common(const void* xs, const void* ys, const void* ps, long n, int H, int W, const void* out) {
+    BMC_REQUIRE(n >= 0 && H > 0 && W > 0, "encoder: bad sizes n=%ld H=%d W=%d", n, H, W);
+    BMC_REQUIRE(out != nullptr, "encoder: out is NULL");
+    BMC_REQUIRE(n == 0 || (xs && ys && ps), "encoder: NULL event array");
+    BMC_REQUIRE((long)H * W * 2 < (1L << 30), "encoder: grid too large");
+    return BMC_OK;
+}
+
+}  // namespace
+}  // namespace bmc
+
+using namespace bmc;
+
+extern "C" BMC_EXPORT size_t bmc_encode_workspace_bytes(int64_t out_elems) { return ws_bytes(out_elems); }
+
+extern "C" BMC_EXPORT int bmc_encode_channels(float* xs, float* ys, const float* ps, int64_t n, int H, int W,
+                                   float* out, void* workspace, size_t workspace_bytes,
+                                   unsigned flags, void* stream) {
+    int rc = check_common(xs, ys, ps, n, H, W, out);
+    if (rc) return rc;
+    ChannelsOp op;
+    op.xs = xs; op.ys = ys; op.ts = nullptr; op.ps = const_cast<float*>(ps);
+    op.H = H; op.W = W; op.bins = 1; op.flags = flags | BMC_ENC_FLIP_Y;
+    return run_scatter(op, n, 2L * H * W, out, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" BMC_EXPORT int bmc_encode_channels_windows(float* xs, float* ys, const float* ps,
+                                           const int64_t* offsets, int n_windows, int H, int W,
+                                           float* out, unsigned flags, void* stream) {
+    BMC_REQUIRE(n_windows >= 0 && H > 0 && W > 0 && out && offsets, "encode_channels_windows: bad args");
+    if (n_windows == 0) return BMC_OK;
+    const size_t smem = (size_t)2 * H * W * 4;
+    BMC_REQUIRE(smem <= (size_t)kSmemBudget,
+                "encode_channels_windows: a [2,%d,%d] window grid exceeds 227 KB of shared memory; "
+                "encode such windows one by one with bmc_encode_channels", H, W);
+    if (smem > 48 * 1024)
+        BMC_CUDA(cudaFuncSetAttribute(channels_windows_kernel,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    channels_windows_kernel<<<n_windows, 256, smem, as_stream(stream)>>>(
+        xs, ys, ps, reinterpret_cast<const long*>(offsets), H, W, out, flags);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+extern "C" BMC_EXPORT int bmc_encode_image(float* xs, float* ys, float* ps, int64_t n, int H, int W,
+                                float* out, void* workspace, size_t workspace_bytes,
+                                unsigned flags, void* stream) {
+    int rc = check_common(xs, ys, ps, n, H, W, out);
+    if (rc) return rc;
+    ImageOp op;
+    op.xs = xs; op.ys = ys; op.ts = nullptr; op.ps = ps;
+    op.H = H; op.W = W; op.bins = 1; op.flags = flags;
+    const long elems = (flags & BMC_ENC_BILINEAR) ? (long)(H + 1) * (W + 1) : (long)H * W;
+    return run_scatter(op, n, elems, out, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" BMC_EXPORT int bmc_encode_voxel(float* xs, float* ys, const float* ts, const float* ps, int64_t n,
+                                int bins, int H, int W, float* out, void* workspace,
+                                size_t workspace_bytes, unsigned flags, void* stream) {
+    int rc = check_common(xs, ys, ps, n, H, W, out);
+    if (rc) return rc;
+    BMC_REQUIRE(bins >= 1 && bins <= 64, "encode_voxel: bins must be in [1,64], got %d", bins);
+    BMC_REQUIRE(n == 0 || ts, "encode_voxel: ts is NULL");
+    VoxelOp op;
+    op.xs = xs; op.ys = ys; op.ts = ts; op.ps = const_cast<float*>(ps);
+    op.H = H; op.W = W; op.bins = bins; op.flags = flags;
+    op.t0 = 0.f; op.dt = 1.f;     // BMC_ENC_TNORM: filled in on the device (VoxelOp::prepare)
+    return run_scatter(op, n, (long)bins * H * W, out, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" BMC_EXPORT int bmc_encode_stack(float* xs, float* ys, const float* ts, float* ps, int64_t n,
+                                int bins, int H, int W, int polarity, float* out, void* workspace,
+                                size_t workspace_bytes, unsigned flags, void* stream) {
+    int rc = check_common(xs, ys, ps, n, H, W, out);
+    if (rc) return rc;
+    BMC_REQUIRE(bins >= 1 && bins <= 64, "encode_stack: bins must be in [1,64], got %d", bins);
+    BMC_REQUIRE(n > 3 && ts, "encode_stack: n <= 3 is the reference's early-out (caller returns zeros)");
+    const long elems = (long)(polarity ? 2 : 1) * bins * H * W;
+    Ws w;
+    rc = carve(workspace, workspace_bytes, elems, w);
+    if (rc) return rc;
+    bin_bounds_kernel<<<1, 128, 0, as_stream(stream)>>>(ts, n, bins, w.beg, w.end);
+    BMC_CUDA(cudaGetLastError());
+    StackOp op;
+    op.xs = xs; op.ys = ys; op.ts = ts; op.ps = ps;
+    op.H = H; op.W = W; op.bins = bins; op.flags = flags & ~BMC_ENC_FLIP_Y;
+    op.beg = w.beg; op.end = w.end; op.polarity = polarity;
+    return run_scatter(op, n, elems, out, workspace, workspace_bytes, as_stream(stream));
+}

@@ -1,0 +1,120 @@
+// Launch descriptors shared by the tensor-core kernels, the SIMT cross-check kernels and the
+// model plan (model.cu).
+//
+// One "conv-gemm" launch computes, for every job j and every row m of B padded images,
+//     out_j[m, :] = act( sum_seg sum_tap A_{j,seg}[m + off_tap, :] . W_j[:, (seg,tap,:)]^T + bias_j )
+//                   (+ residual_j[m, :]),   halo / tail rows forced to zero,
+// which covers the 3x3 and 1x1 convolutions of the reference (models/BMCNet.py:40-53,
+// models/submodules.py:25-26,44-53), their channel concatenations (torch.cat -> K segments),
+// and the `softmax(att) @ v` product of BIE (submodules.py:72-73; per-image dynamic weights).
+//
+// Weights are bf16 in "chunk-major" form: [K/64][w_rows][64], so the B tile of a K chunk is one
+// contiguous [N x 64] box and every weight of the model lives in one tall [rows][64] matrix
+// behind a single TMA descriptor.
+#pragma once
+#include "common.cuh"
+
+namespace bmc {
+
+constexpr int kMaxSeg = 4;
+constexpr int kMaxJobs = 8;
+constexpr int kMaxMaps = 8;
+constexpr int kTileM = 128;
+constexpr int kChunkK = 64;
+
+struct GemmJobDev {
+    int a_map[kMaxSeg];        // index into GemmParams::maps
+    int a_row_base[kMaxSeg];   // row of the source paired with output row 0
+    int a_col_base[kMaxSeg];   // first channel used
+    const __nv_bfloat16* a_ptr[kMaxSeg];   // same sources as raw pointers (SIMT kernel)
+    int a_ld[kMaxSeg];
+    long a_rows[kMaxSeg];
+    int w_map;
+    const __nv_bfloat16* w_ptr;
+    int w_rows;                // rows per K chunk of the weight matrix behind w_map / w_ptr
+    int w_row_base;
+    int w_img_stride;
+    const float* bias;
+    const __nv_bfloat16* residual;
+    long res_row_base;
+    __nv_bfloat16* out;
+    long out_row_base;
+    float* out_f32;
+    int relu;
+    // fused channel LayerNorm on (acc + bias) before the store (submodules.py:127-139,
+    // `norm_s(convf(...))` at :63-64); N = 128 only
+    const float* ln_gamma;
+    const float* ln_beta;
+    float ln_eps;
+};
+
+struct alignas(64) GemmParams {
+    CUtensorMap maps[kMaxMaps];
+    GemmJobDev jobs[kMaxJobs];
+    int n_jobs;
+    int n_seg;
+    int chunks[kMaxSeg];       // 64-channel chunks per segment
+    int n_taps;
+    int tap_off[9];            // row shift of each tap: dy*Wp + dx
+    int n;                     // output channels: 128 or 32
+    Geom g;
+    int tiles_per_img;         // R / 128
+};
+
+static_assert(sizeof(GemmParams) <= 4096, "GemmParams must fit the classic 4 KB kernel parameter space");
+
+// att[b] = centres[b]^T . v[b] (split over pixel ranges) -- submodules.py:69-70
+constexpr int kMaxPairs = 4;
+struct alignas(64) AttParams {
+    CUtensorMap map_c, map_v;              // box [64 pixel rows][64 channels] over [rows][128]
+    long c_row_base[kMaxPairs], v_row_base[kMaxPairs];
+    const __nv_bfloat16* c_ptr; const __nv_bfloat16* v_ptr;   // raw bases (SIMT kernel)
+    int n_pairs, n_split;
+    int pix_per_split;                     // multiple of 64
+    float scale;
+    float* partial;                        // [pair][B][split][128][128]
+    Geom g;
+};
+
+struct SoftmaxParams {
+    const float* partial;                  // as above
+    int n_pairs, n_split, B;
+    __nv_bfloat16* w_base;                 // [rows][64] dynamic-weight arena; P of (pair, b) is the
+    int w_row_base[kMaxPairs];             // chunk-major block [2][128][64] starting at row
+    int w_img_stride;                      // w_row_base[pair] + b * w_img_stride
+};
+
+// Launchers (host).  `impl`: 0 = tcgen05/TMA, 1 = SIMT cross-check.
+int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st);
+int launch_att(const AttParams& p, int impl, cudaStream_t st);
+int launch_att_softmax(const SoftmaxParams& p, cudaStream_t st);
+
+// Pointwise kernels (pointwise.cu)
+int launch_layernorm(const __nv_bfloat16* in, const float* gamma, const float* beta, float eps,
+                     long rows, __nv_bfloat16* out, cudaStream_t st);
+int launch_pack_nchw(const float* src, Geom g, int C, __nv_bfloat16* dst, int c_pad, int c_off,
+                     cudaStream_t st);
+int launch_unpack_nchw(const __nv_bfloat16* src, Geom g, int C, int c_pad, int c_off, float* dst,
+                       cudaStream_t st);
+struct PackInputsParams {
+    const float* x; long xs[5];            // [B,2,T,H,W] element strides
+    const float* x_o;                      // [B,32,H,W] (init) or [B,2,4H,4W]; NULL = keep the o part
+                                           // already in `mi` (or zero it when init)
+    int init;
+    __nv_bfloat16* mi;                     // [B*R][64]
+    Geom g;
+};
+int launch_pack_inputs(const PackInputsParams& p, cudaStream_t st);
+struct EmitParams {
+    const float* a;                        // conv_o result, fp32 [B*R][32]
+    const float* x; long xs[5];            // f2 = x[:, :, 1]
+    float* out_o;                          // [B,2,4H,4W] or NULL
+    __nv_bfloat16* mi_next;                // o part of the next step's input tensor, or NULL
+    Geom g;
+};
+int launch_emit(const EmitParams& p, cudaStream_t st);
+int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out,
+                         int n_out_pad, int K, __nv_bfloat16* dst, int w_rows, int w_row_base,
+                         cudaStream_t st);
+
+}  // namespace bmc

@@ -1,0 +1,357 @@
+// tcgen05 / TMEM / TMA kernels for sm_100a: the implicit-GEMM convolution and the BIE
+// attention-logit GEMM.
+//
+// conv_gemm_tc:  one CTA per 128-row tile of padded pixels, N (=128 or 32) output channels.
+//   warp 0      TMA producer: per K step one [128 x 64] activation box (row coordinate shifted
+//               by the tap offset -- out-of-range rows arrive as zeros) and one [N x 64] weight box
+//   warp 1      TMEM allocation + single-thread tcgen05.mma issue (M=128, N, K=16, bf16 -> fp32)
+//   warps 2-5   epilogue: tcgen05.ld (one accumulator row per thread), bias / ReLU / residual /
+//               halo masking, bf16 (and optional fp32) stores
+//   smem ring of kStages {A 16 KB, B N*128 B} tiles in the 128-byte-swizzled K-major layout, full /
+//   empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it are done.
+#include "gemm.cuh"
+
+namespace bmc {
+namespace {
+
+constexpr int kThreadsTc = 192;
+
+template <int N>
+struct TcCfg {
+    static constexpr int kABytes = kTileM * kChunkK * 2;   // 16384
+    static constexpr int kBBytes = N * kChunkK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kTmemCols = N < 32 ? 32 : N;      // power of two >= 32
+};
+
+template <int N, int STAGES>
+__global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant__ GemmParams p) {
+    using Cfg = TcCfg<N>;
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    // dynamic smem base is only guaranteed 16-byte aligned: realign to 1024 for SWIZZLE_128B
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float bias_s[N], gamma_s[N], beta_s[N];
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const GemmJobDev& job = p.jobs[blockIdx.y];
+    const int tile = blockIdx.x;
+    const long m0 = (long)tile * kTileM;
+    const int img = tile / p.tiles_per_img;
+
+    int iters = 0;
+    for (int s = 0; s < p.n_seg; ++s) iters += p.n_taps * p.chunks[s];
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        mbar_fence_init();
+        for (int s = 0; s < p.n_seg; ++s) tma_prefetch_desc(&p.maps[job.a_map[s]]);
+        tma_prefetch_desc(&p.maps[job.w_map]);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, Cfg::kTmemCols);
+    if (threadIdx.x >= 64 && threadIdx.x - 64 < N) {
+        const int n = threadIdx.x - 64;
+        bias_s[n] = job.bias ? job.bias[n] : 0.f;
+        gamma_s[n] = job.ln_gamma ? job.ln_gamma[n] : 1.f;
+        beta_s[n] = job.ln_gamma ? job.ln_beta[n] : 0.f;
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_acc = tmem_base_s;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            const int w_row0 = job.w_row_base + img * job.w_img_stride;
+            int it = 0, kchunk = 0;
+            for (int s = 0; s < p.n_seg; ++s) {
+                const CUtensorMap* amap = &p.maps[job.a_map[s]];
+                for (int t = 0; t < p.n_taps; ++t) {
+                    const int arow = job.a_row_base[s] + (int)m0 + p.tap_off[t];
+                    for (int c = 0; c < p.chunks[s]; ++c, ++it, ++kchunk) {
+                        const int st = it % STAGES;
+                        if (it >= STAGES) mbar_wait(&empty_bar[st], ((it / STAGES) - 1) & 1);
+                        uint8_t* sa = smem + st * Cfg::kStageBytes;
+                        mbar_expect_tx(&full_bar[st], Cfg::kStageBytes);
+                        tma_load_2d(sa, amap, &full_bar[st], job.a_col_base[s] + c * kChunkK, arow);
+                        tma_load_2d(sa + Cfg::kABytes, &p.maps[job.w_map], &full_bar[st], 0,
+                                    kchunk * job.w_rows + w_row0);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N, false, false);
+            for (int it = 0; it < iters; ++it) {
+                const int st = it % STAGES;
+                mbar_wait(&full_bar[st], (it / STAGES) & 1);
+                tc_fence_after_sync();
+                const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
+                const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+                for (int k = 0; k < kChunkK / 16; ++k) {
+                    // K-major SWIZZLE_128B: 8-row groups 1024 B apart; +32 B per K=16 slice
+                    const uint64_t da = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
+                    const uint64_t db = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
+                    umma_f16(tmem_acc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[st]);       // stage reusable once these MMAs retire
+            }
+            umma_commit(&acc_bar);                 // accumulator complete
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int r_tile = q * 32 + lane;
+        const long m = m0 + r_tile;
+        const int r_img = (int)(m - (long)img * p.g.R);
+        int y, x;
+        const bool valid = p.g.interior(r_img, y, x);
+        mbar_wait(&acc_bar, 0);
+        tc_fence_after_sync();
+        const __nv_bfloat16* res = job.residual ? job.residual + (job.res_row_base + m) * N : nullptr;
+        __nv_bfloat16* out = job.out ? job.out + (job.out_row_base + m) * N : nullptr;
+        float* outf = job.out_f32 ? job.out_f32 + (job.out_row_base + m) * N : nullptr;
+        const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
+        // Fused channel LayerNorm: this thread owns the whole row, so mean / variance are
+        // thread-local; two extra passes over TMEM (16 TB/s) instead of an HBM round trip.
+        const bool ln = job.ln_gamma != nullptr;
+        float mu = 0.f, rstd = 1.f;
+        if (ln) {
+            float s1 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(trow + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) s1 += __uint_as_float(v[j]) + bias_s[c * 32 + j];
+            }
+            mu = s1 * (1.f / N);
+            float s2 = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < N / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld_32x32(trow + c * 32, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float d = __uint_as_float(v[j]) + bias_s[c * 32 + j] - mu;
+                    s2 += d * d;
+                }
+            }
+            rstd = 1.f / sqrtf(s2 * (1.f / N) + job.ln_eps);
+        }
+#pragma unroll 1
+        for (int c = 0; c < N / 32; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(trow + c * 32, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                f[j] = __uint_as_float(v[j]) + bias_s[c * 32 + j];
+                if (ln) f[j] = gamma_s[c * 32 + j] * ((f[j] - mu) * rstd) + beta_s[c * 32 + j];
+                if (job.relu) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (res) {
+                const uint4* rp = reinterpret_cast<const uint4*>(res + c * 32);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const uint4 rv = valid ? rp[u] : make_uint4(0, 0, 0, 0);
+                    const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 t = unpack_bf16x2(w[e]);
+                        f[u * 8 + e * 2] += t.x;
+                        f[u * 8 + e * 2 + 1] += t.y;
+                    }
+                }
+            }
+            if (!valid) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = 0.f;
+            }
+            if (out) {
+                uint4* op = reinterpret_cast<uint4*>(out + c * 32);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    op[u] = make_uint4(pack_bf16x2(f[u * 8], f[u * 8 + 1]), pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]),
+                                       pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]), pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]));
+            }
+            if (outf) {
+                float4* op = reinterpret_cast<float4*>(outf + c * 32);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) op[u] = make_float4(f[u * 4], f[u * 4 + 1], f[u * 4 + 2], f[u * 4 + 3]);
+            }
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_acc, Cfg::kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------- attention logits
+// D[c, c'] = sum_p centres[p, c] * v[p, c'] over a range of pixels of one image: both operands
+// are "MN-major" (the contraction index p is the slow, row index of the [rows][128] tensors).
+// smem tile per operand and stage: two [64 pixels x 64 channels] SWIZZLE_128B boxes (8 KB each).
+constexpr int kAttStages = 4;
+constexpr int kAttBox = 64 * 64 * 2;             // 8192
+constexpr int kAttStageBytes = 4 * kAttBox;      // c lo/hi, v lo/hi
+
+__global__ void __launch_bounds__(kThreadsTc) att_tc(const __grid_constant__ AttParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t full_bar[kAttStages], empty_bar[kAttStages], acc_bar;
+    __shared__ uint32_t tmem_base_s;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int split = blockIdx.x, b = blockIdx.y, pair = blockIdx.z;
+    const int pix0 = split * p.pix_per_split;
+    const int pix1 = min(pix0 + p.pix_per_split, p.g.R);
+    const int iters = (pix1 - pix0) / 64;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kAttStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        mbar_init(&acc_bar, 1);
+        mbar_fence_init();
+        tma_prefetch_desc(&p.map_c);
+        tma_prefetch_desc(&p.map_v);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 128);
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_acc = tmem_base_s;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int crow = (int)(p.c_row_base[pair] + (long)b * p.g.R) + pix0;
+            const int vrow = (int)(p.v_row_base[pair] + (long)b * p.g.R) + pix0;
+            for (int it = 0; it < iters; ++it) {
+                const int st = it % kAttStages;
+                if (it >= kAttStages) mbar_wait(&empty_bar[st], ((it / kAttStages) - 1) & 1);
+                uint8_t* s0 = smem + st * kAttStageBytes;
+                mbar_expect_tx(&full_bar[st], kAttStageBytes);
+                tma_load_2d(s0, &p.map_c, &full_bar[st], 0, crow + it * 64);
+                tma_load_2d(s0 + kAttBox, &p.map_c, &full_bar[st], 64, crow + it * 64);
+                tma_load_2d(s0 + 2 * kAttBox, &p.map_v, &full_bar[st], 0, vrow + it * 64);
+                tma_load_2d(s0 + 3 * kAttBox, &p.map_v, &full_bar[st], 64, vrow + it * 64);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 128, true, true);
+            for (int it = 0; it < iters; ++it) {
+                const int st = it % kAttStages;
+                mbar_wait(&full_bar[st], (it / kAttStages) & 1);
+                tc_fence_after_sync();
+                const uint32_t sa = smem_u32(smem + st * kAttStageBytes);
+                const uint32_t sb = sa + 2 * kAttBox;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    // MN-major SWIZZLE_128B: 64-channel blocks LBO = 8192 B apart, 8-pixel groups
+                    // SBO = 1024 B apart; one K=16 slice = 16 pixel rows = 2048 B.
+                    const uint64_t da = umma_smem_desc_sw128(sa + k * 2048, kAttBox, 1024);
+                    const uint64_t db = umma_smem_desc_sw128(sb + k * 2048, kAttBox, 1024);
+                    umma_f16(tmem_acc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[st]);
+            }
+            umma_commit(&acc_bar);
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;             // centre channel c
+        float* dst = p.partial + ((((long)pair * p.g.B + b) * p.n_split + split) * 128 + row) * 128;
+        if (iters > 0) {
+            mbar_wait(&acc_bar, 0);
+            tc_fence_after_sync();
+        }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            if (iters > 0) {
+                tmem_ld_32x32(tmem_acc + ((uint32_t)(q * 32) << 16) + c * 32, v);
+                tmem_ld_wait();
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0;
+            }
+            float4* op = reinterpret_cast<float4*>(dst + c * 32);
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                op[u] = make_float4(__uint_as_float(v[u * 4]) * p.scale, __uint_as_float(v[u * 4 + 1]) * p.scale,
+                                    __uint_as_float(v[u * 4 + 2]) * p.scale, __uint_as_float(v[u * 4 + 3]) * p.scale);
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_acc, 128);
+    }
+}
+
+template <int N, int STAGES>
+int launch_tc(const GemmParams& p, cudaStream_t st) {
+    auto kern = conv_gemm_tc<N, STAGES>;
+    const int smem = STAGES * TcCfg<N>::kStageBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)(p.g.B * p.tiles_per_img), (unsigned)p.n_jobs);
+    kern<<<grid, kThreadsTc, smem, st>>>(p);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+}  // namespace
+
+int launch_conv_gemm_simt(const GemmParams& p, cudaStream_t st);
+int launch_att_simt(const AttParams& p, cudaStream_t st);
+
+int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
+    if (impl == 1) return launch_conv_gemm_simt(p, st);
+    static int stages = 0;
+    if (stages == 0) {
+        const char* e = getenv("BMC_TC_STAGES");
+        stages = e ? atoi(e) : 3;
+        if (stages != 3 && stages != 4 && stages != 6) stages = 3;
+    }
+    if (p.n == 128) {
+        if (stages == 6) return launch_tc<128, 6>(p, st);
+        if (stages == 4) return launch_tc<128, 4>(p, st);
+        return launch_tc<128, 3>(p, st);
+    }
+    if (p.n == 32) return launch_tc<32, 4>(p, st);
+    set_error("conv_gemm: unsupported N=%d (128 or 32)", p.n);
+    return BMC_ERR_UNSUPPORTED;
+}
+
+int launch_att(const AttParams& p, int impl, cudaStream_t st) {
+    if (impl == 1) return launch_att_simt(p, st);
+    const int smem = kAttStages * kAttStageBytes + 1024;
+    static bool configured = false;
+    if (!configured) {
+        BMC_CUDA(cudaFuncSetAttribute(att_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)p.n_split, (unsigned)p.g.B, (unsigned)p.n_pairs);
+    att_tc<<<grid, kThreadsTc, smem, st>>>(p);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+}  // namespace bmc

@@ -1,0 +1,251 @@
+// Layout / pointwise kernels around the GEMMs: fp32 NCHW <-> padded NHWC bf16, the per-step input
+// tensor, channel LayerNorm, x4 PixelShuffle + bilinear reconstruction, weight repacking.
+#include "gemm.cuh"
+
+namespace bmc {
+namespace {
+
+// ---------------------------------------------------------------- LayerNorm over 128 channels
+// submodules.py:127-139: mu, biased var, (x-mu)/sqrt(var+eps)*w+b.  One warp per row, 4 ch / lane.
+__global__ void layernorm_rows(const __nv_bfloat16* __restrict__ in, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps, long rows,
+                               __nv_bfloat16* __restrict__ out) {
+    const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const uint2 raw = *reinterpret_cast<const uint2*>(in + row * 128 + lane * 4);
+    const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+    float s = a.x + a.y + b.x + b.y;
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mu = s * (1.f / 128.f);
+    const float d0 = a.x - mu, d1 = a.y - mu, d2 = b.x - mu, d3 = b.y - mu;
+    float v = d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const float rstd = 1.f / sqrtf(v * (1.f / 128.f) + eps);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + lane * 4);
+    const float4 bt = *reinterpret_cast<const float4*>(beta + lane * 4);
+    uint2 o2;
+    o2.x = pack_bf16x2(g.x * (d0 * rstd) + bt.x, g.y * (d1 * rstd) + bt.y);
+    o2.y = pack_bf16x2(g.z * (d2 * rstd) + bt.z, g.w * (d3 * rstd) + bt.w);
+    *reinterpret_cast<uint2*>(out + row * 128 + lane * 4) = o2;
+}
+
+// ---------------------------------------------------------------- NCHW fp32 -> padded NHWC bf16
+// thread = (pixel, 8-channel group); lanes run over pixels so the NCHW reads coalesce.
+__global__ void pack_nchw(const float* __restrict__ src, Geom g, int C, __nv_bfloat16* __restrict__ dst,
+                          int c_pad, int c_off) {
+    const int HW = g.H * g.W;
+    const int groups = (C + 7) / 8;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per_img = (long)HW * groups;
+    if (idx >= per_img * g.B) return;
+    const int b = (int)(idx / per_img);
+    const long r = idx - (long)b * per_img;
+    const int grp = (int)(r / HW);
+    const int pix = (int)(r - (long)grp * HW);
+    const int y = pix / g.W, x = pix - y * g.W;
+    const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
+    const float* s = src + ((long)b * C + grp * 8) * HW + pix;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (grp * 8 + j < C) ? s[(long)j * HW] : 0.f;
+    __nv_bfloat16* d = dst + row * c_pad + c_off + grp * 8;
+    if (grp * 8 + 8 <= C && ((c_off & 7) == 0)) {
+        *reinterpret_cast<uint4*>(d) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+    } else {
+        for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[j] = __float2bfloat16(f[j]);
+    }
+}
+
+__global__ void unpack_nchw(const __nv_bfloat16* __restrict__ src, Geom g, int C, int c_pad, int c_off,
+                            float* __restrict__ dst) {
+    const int HW = g.H * g.W;
+    const int groups = (C + 7) / 8;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per_img = (long)HW * groups;
+    if (idx >= per_img * g.B) return;
+    const int b = (int)(idx / per_img);
+    const long r = idx - (long)b * per_img;
+    const int grp = (int)(r / HW);
+    const int pix = (int)(r - (long)grp * HW);
+    const int y = pix / g.W, x = pix - y * g.W;
+    const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
+    const __nv_bfloat16* s = src + row * c_pad + c_off + grp * 8;
+    float* d = dst + ((long)b * C + grp * 8) * HW + pix;
+    for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[(long)j * HW] = __bfloat162float(s[j]);
+}
+
+// ---------------------------------------------------------------- per-step input tensor "MI"
+// 64 bf16 channels per padded pixel:
+//   0-2  f1 positive x3 | 3-5  f2 positive x3 | 6-8  f1 negative x3 | 9-11 f2 negative x3
+//   (the `.repeat(1, 3, 1, 1)` planes of BMCNet.py:109-112 / BMCNet_plain.py:57-58)
+//   12-43 the 32 feedback channels o: x_o itself when init, else pixel_unshuffle(x_o, 4)
+//         (BMCNet.py:117, submodules.py:80-92: channel = c*16 + ry*4 + rx)
+//   44-63 zero
+__global__ void pack_inputs(PackInputsParams p) {
+    const Geom g = p.g;
+    const int HW = g.H * g.W;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)g.B * HW) return;
+    const int b = (int)(idx / HW);
+    const int pix = (int)(idx - (long)b * HW);
+    const int y = pix / g.W, x = pix - y * g.W;
+    __nv_bfloat16* d = p.mi + ((long)b * g.R + (long)(y + 1) * g.Wp + (x + 1)) * 64;
+    const float* xb = p.x + b * p.xs[0] + y * p.xs[3] + x * p.xs[4];
+    const float f1p = xb[0], f2p = xb[p.xs[2]];
+    const float f1n = xb[p.xs[1]], f2n = xb[p.xs[1] + p.xs[2]];
+    const uint32_t w1p = pack_bf16x2(f1p, f1p), w2p = pack_bf16x2(f2p, f2p);
+    const uint32_t w1n = pack_bf16x2(f1n, f1n), w2n = pack_bf16x2(f2n, f2n);
+    uint32_t* dw = reinterpret_cast<uint32_t*>(d);
+    dw[0] = w1p; dw[1] = pack_bf16x2(f1p, f2p); dw[2] = w2p;
+    dw[3] = w1n; dw[4] = pack_bf16x2(f1n, f2n); dw[5] = w2n;
+    if (!p.x_o && p.init) {                      // device-resident recurrence, reset: o = 0
+#pragma unroll
+        for (int c = 6; c < 32; ++c) dw[c] = 0u;
+    }
+    if (p.x_o) {
+        float o[32];
+        if (p.init) {
+            const float* s = p.x_o + (long)b * 32 * HW + pix;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) o[c] = s[(long)c * HW];
+        } else {
+            const int HW4 = 16 * HW, W4 = 4 * g.W;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int ry = 0; ry < 4; ++ry) {
+                    const float4 v = *reinterpret_cast<const float4*>(
+                        p.x_o + ((long)b * 2 + c) * HW4 + (long)(4 * y + ry) * W4 + 4 * x);
+                    o[c * 16 + ry * 4 + 0] = v.x; o[c * 16 + ry * 4 + 1] = v.y;
+                    o[c * 16 + ry * 4 + 2] = v.z; o[c * 16 + ry * 4 + 3] = v.w;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+#pragma unroll
+        for (int c = 22; c < 32; ++c) dw[c] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------- reconstruction
+// x_o = pixel_shuffle(a, 4) + bilinear_x4(f2)  (BMCNet.py:119, BMCNet_plain.py:66), fp32.
+// F.interpolate(mode='bilinear', align_corners=False, scale_factor=4): src = (dst+0.5)/4-0.5
+// clamped at 0, neighbours clamped at the border.  One thread per LR pixel: 2x4x4 outputs.
+// Also writes the next step's feedback channels: pixel_unshuffle of what was just produced.
+__device__ __forceinline__ void lerp_taps(int d, int n, int& i0, int& i1, float& l1) {
+    float s = (d + 0.5f) * 0.25f - 0.5f;
+    if (s < 0.f) s = 0.f;
+    i0 = (int)s;
+    i1 = i0 + (i0 < n - 1 ? 1 : 0);
+    l1 = s - (float)i0;
+}
+__global__ void emit_output(EmitParams p) {
+    const Geom g = p.g;
+    const int HW = g.H * g.W;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)g.B * HW) return;
+    const int b = (int)(idx / HW);
+    const int pix = (int)(idx - (long)b * HW);
+    const int y = pix / g.W, x = pix - y * g.W;
+    const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
+    const float* a = p.a + row * 32;
+    float o[32];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        const float* f2 = p.x + b * p.xs[0] + c * p.xs[1] + p.xs[2];
+#pragma unroll
+        for (int ry = 0; ry < 4; ++ry) {
+            int y0, y1; float ly;
+            lerp_taps(4 * y + ry, g.H, y0, y1, ly);
+#pragma unroll
+            for (int rx = 0; rx < 4; ++rx) {
+                int x0, x1; float lx;
+                lerp_taps(4 * x + rx, g.W, x0, x1, lx);
+                const float v00 = f2[y0 * p.xs[3] + x0 * p.xs[4]], v01 = f2[y0 * p.xs[3] + x1 * p.xs[4]];
+                const float v10 = f2[y1 * p.xs[3] + x0 * p.xs[4]], v11 = f2[y1 * p.xs[3] + x1 * p.xs[4]];
+                const float up = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
+                o[c * 16 + ry * 4 + rx] = a[c * 16 + ry * 4 + rx] + up;
+            }
+        }
+    }
+    if (p.out_o) {
+        const int W4 = 4 * g.W;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+            for (int ry = 0; ry < 4; ++ry)
+                *reinterpret_cast<float4*>(p.out_o + ((long)b * 2 + c) * 16 * HW + (long)(4 * y + ry) * W4 + 4 * x) =
+                    make_float4(o[c * 16 + ry * 4], o[c * 16 + ry * 4 + 1], o[c * 16 + ry * 4 + 2], o[c * 16 + ry * 4 + 3]);
+    }
+    if (p.mi_next) {
+        uint32_t* dw = reinterpret_cast<uint32_t*>(p.mi_next + row * 64);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+    }
+}
+
+// ---------------------------------------------------------------- weight repack
+// fp32 conv weight [n_out][*] -> bf16 chunk-major [K/64][w_rows][64] at rows
+// [w_row_base, w_row_base + n_out_pad); kmap[k] = flat offset inside one output-channel row of
+// the source, or -1 for zero padding.
+__global__ void repack_weight(const float* __restrict__ src, const int* __restrict__ kmap, int src_row_len,
+                              int n_out, int n_out_pad, int K, __nv_bfloat16* __restrict__ dst, int w_rows,
+                              int w_row_base) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)n_out_pad * K) return;
+    const int n = (int)(idx / K), k = (int)(idx - (long)n * K);
+    const int off = kmap[k];
+    const float v = (n < n_out && off >= 0) ? src[(long)n * src_row_len + off] : 0.f;
+    dst[((long)(k >> 6) * w_rows + w_row_base + n) * 64 + (k & 63)] = __float2bfloat16(v);
+}
+
+}  // namespace
+
+int launch_layernorm(const __nv_bfloat16* in, const float* gamma, const float* beta, float eps, long rows,
+                     __nv_bfloat16* out, cudaStream_t st) {
+    if (rows <= 0) return BMC_OK;
+    layernorm_rows<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(in, gamma, beta, eps, rows, out);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_pack_nchw(const float* src, Geom g, int C, __nv_bfloat16* dst, int c_pad, int c_off, cudaStream_t st) {
+    const long total = (long)g.B * g.H * g.W * ((C + 7) / 8);
+    pack_nchw<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, g, C, dst, c_pad, c_off);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_unpack_nchw(const __nv_bfloat16* src, Geom g, int C, int c_pad, int c_off, float* dst, cudaStream_t st) {
+    const long total = (long)g.B * g.H * g.W * ((C + 7) / 8);
+    unpack_nchw<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, g, C, c_pad, c_off, dst);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_pack_inputs(const PackInputsParams& p, cudaStream_t st) {
+    const long total = (long)p.g.B * p.g.H * p.g.W;
+    pack_inputs<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_emit(const EmitParams& p, cudaStream_t st) {
+    const long total = (long)p.g.B * p.g.H * p.g.W;
+    emit_output<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out, int n_out_pad, int K,
+                            __nv_bfloat16* dst, int w_rows, int w_row_base, cudaStream_t st) {
+    const long total = (long)n_out_pad * K;
+    repack_weight<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kmap, src_row_len, n_out, n_out_pad, K, dst,
+                                                                  w_rows, w_row_base);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+}  // namespace bmc

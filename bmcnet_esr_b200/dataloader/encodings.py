@@ -1,0 +1,201 @@
+"""Event encoders -- drop-in for the forward encoders of the reference `dataloader/encodings.py`
+(:6-305): same names, signatures, return shapes and in-place side effects, computed by the
+sm_100a histogram kernels of libbmc_b200 (csrc/encode.cu) on CUDA float32 tensors.
+
+Differences a caller can observe:
+  * inputs must live on a CUDA device (the reference runs these inside CPU dataloader workers;
+    there is no CPU fallback here) and must be contiguous float32 (the reference's input contract,
+    base_dataset.py:24-31);
+  * count-valued encodings are bit-exact; float-weighted ones (events_to_voxel*, weighted
+    events_to_image*) accumulate in a different order than the reference's serial loop and agree
+    to ~1e-6 relative;
+  * NaN coordinates are dropped (the reference indexes with garbage).
+Reproduced on purpose (bit-exact parity): out-of-range events are zeroed in the
+caller's xs / ys (/ ps), the leak of such events into pixel (0,0) on later passes, and the double
+counting of bin-boundary events by the any-equal binary search.
+"""
+import ctypes as C
+
+import torch
+
+from .. import _lib
+from .._lib import check, lib, stream_ptr
+
+__all__ = ['interpolate_to_image', 'events_to_image_torch', 'binary_search_torch_tensor',
+           'events_to_voxel_torch', 'events_to_stack_polarity', 'events_to_stack_no_polarity',
+           'events_to_image', 'events_to_voxel', 'events_to_channels', 'events_to_channels_windows']
+
+_MUT = _lib.ENC_MUTATE
+
+
+def _chk(*ts):
+    n = None
+    for t in ts:
+        if not isinstance(t, torch.Tensor) or not t.is_cuda:
+            raise _lib.BmcError('encoders need CUDA tensors (no CPU fallback), got %s' % (
+                t.device if isinstance(t, torch.Tensor) else type(t)))
+        if t.dtype != torch.float32 or t.dim() != 1 or not t.is_contiguous():
+            raise _lib.BmcError('encoders need contiguous 1-D float32 event tensors (base_dataset.py:24-31), got '
+                                '%s %s' % (t.dtype, tuple(t.shape)))
+        n = len(t) if n is None else n
+    return n
+
+
+def _run(fn, out, *args):
+    """Call an encoder entry with a scratch workspace sized for `out`."""
+    nbytes = lib().bmc_encode_workspace_bytes(out.numel())
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=out.device)
+    with torch.cuda.device(out.device):
+        check(fn(*args, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes))
+    return out
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def events_to_image(xs, ys, ps, sensor_size=(180, 240)):
+    """Accumulate events into a y-flipped [H,W] image (reference encodings.py:241-269).
+    Out-of-range events are zeroed in xs, ys AND ps, as the reference does."""
+    n = _chk(xs, ys, ps)
+    h, w = sensor_size
+    out = torch.empty(h, w, dtype=torch.float32, device=xs.device)
+    flags = _lib.ENC_FLIP_Y | _MUT
+    return _run(lambda *a: lib().bmc_encode_image(_p(xs), _p(ys), _p(ps), n, h, w, *a, flags, stream_ptr()), out)
+
+
+def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
+    """Two-channel event counters [2,H,W] (reference encodings.py:290-305) -- the encoder on the
+    live inference / training path (h5dataset.py:518-526)."""
+    assert len(xs) == len(ys) and len(ys) == len(ps)
+    n = _chk(xs, ys, ps)
+    h, w = sensor_size
+    out = torch.empty(2, h, w, dtype=torch.float32, device=xs.device)
+    return _run(lambda *a: lib().bmc_encode_channels(_p(xs), _p(ys), _p(ps), n, h, w, *a, _MUT, stream_ptr()), out)
+
+
+def events_to_channels_windows(xs, ys, ps, offsets, sensor_size=(180, 240)):
+    """Batched events_to_channels: window i = events [offsets[i], offsets[i+1]) -> out[i] = [2,H,W].
+    (Not in the reference; it is the dataloader's per-window loop, h5dataset.py:261-316, in one launch.)"""
+    _chk(xs, ys, ps)
+    if offsets.dtype != torch.int64 or not offsets.is_cuda:
+        raise _lib.BmcError('offsets must be a CUDA int64 tensor')
+    h, w = sensor_size
+    nw = len(offsets) - 1
+    out = torch.empty(nw, 2, h, w, dtype=torch.float32, device=xs.device)
+    with torch.cuda.device(xs.device):
+        check(lib().bmc_encode_channels_windows(_p(xs), _p(ys), _p(ps), _p(offsets), nw, h, w, _p(out), _MUT,
+                                                stream_ptr()))
+    return out
+
+
+def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240)):
+    """Temporal-bilinear voxel grid [B,H,W], y-flipped (reference encodings.py:272-287)."""
+    assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
+    n = _chk(xs, ys, ts, ps)
+    h, w = sensor_size
+    out = torch.empty(num_bins, h, w, dtype=torch.float32, device=xs.device)
+    flags = _lib.ENC_FLIP_Y | _MUT
+    return _run(lambda *a: lib().bmc_encode_voxel(_p(xs), _p(ys), _p(ts), _p(ps), n, num_bins, h, w, *a, flags,
+                                                  stream_ptr()), out)
+
+
+def interpolate_to_image(pxs, pys, dxs, dys, weights, img):
+    """Bilinear splat of weighted points into `img` (reference encodings.py:6-13).  Helper kept for
+    API completeness; events_to_image_torch(interpolation='bilinear') does this inside its kernel."""
+    img.index_put_((pys, pxs), weights * (1.0 - dxs) * (1.0 - dys), accumulate=True)
+    img.index_put_((pys, pxs + 1), weights * dxs * (1.0 - dys), accumulate=True)
+    img.index_put_((pys + 1, pxs), weights * (1.0 - dxs) * dys, accumulate=True)
+    img.index_put_((pys + 1, pxs + 1), weights * dxs * dys, accumulate=True)
+
+
+def events_to_image_torch(xs, ys, ps, device=None, sensor_size=(180, 240), clip_out_of_range=True,
+                          interpolation=None, padding=True):
+    """Event image without y-flip (reference encodings.py:16-72).  `interpolation='bilinear'`
+    (with padding) splats into a (H+1)x(W+1) image.  Mutates xs, ys, ps like the reference."""
+    n = _chk(xs, ys, ps)
+    h, w = sensor_size
+    flags = _MUT
+    if interpolation == 'bilinear':
+        if not padding:
+            raise NotImplementedError('bilinear interpolation without padding (unused by the reference callers)')
+        flags |= _lib.ENC_BILINEAR
+        out = torch.empty(h + 1, w + 1, dtype=torch.float32, device=xs.device)
+    else:
+        out = torch.empty(h, w, dtype=torch.float32, device=xs.device)
+    out = _run(lambda *a: lib().bmc_encode_image(_p(xs), _p(ys), _p(ps), n, h, w, *a, flags, stream_ptr()), out)
+    return out if device is None else out.to(device)
+
+
+def binary_search_torch_tensor(t, l, r, x, side='left'):
+    """The reference's any-equal binary search (encodings.py:75-97), element reads on the host.
+    The stack encoders below evaluate the same search on the device instead."""
+    if r is None:
+        r = len(t) - 1
+    while l <= r:
+        if t[l] == x:
+            return l
+        if t[r] == x:
+            return r
+        mid = l + (r - l) // 2
+        midval = t[mid]
+        if midval == x:
+            return mid
+        elif midval < x:
+            l = mid + 1
+        else:
+            r = mid - 1
+    return l if side == 'left' else r
+
+
+def _early_out(ts, B, sensor_size, device):
+    # reference encodings.py:122-123,166-167,217-218: [B,H,W] zeros, also for the polarity stack
+    if len(ts) <= 3 or bool((ts == 0).all()):
+        return torch.zeros([B, sensor_size[0], sensor_size[1]], device=device)
+    return None
+
+
+def _stack(xs, ys, ts, ps, B, device, sensor_size, polarity):
+    if device is None:
+        device = xs.device
+    n = _chk(xs, ys, ts, ps)
+    eo = _early_out(ts, B, sensor_size, device)
+    if eo is not None:
+        return eo
+    assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
+    h, w = sensor_size
+    shape = (2, B, h, w) if polarity else (B, h, w)
+    out = torch.empty(*shape, dtype=torch.float32, device=xs.device)
+    out = _run(lambda *a: lib().bmc_encode_stack(_p(xs), _p(ys), _p(ts), _p(ps), n, B, h, w, int(polarity), *a,
+                                                 _MUT, stream_ptr()), out)
+    return out.to(device)
+
+
+def events_to_stack_polarity(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)):
+    """[2,B,H,W] per-polarity counts per time bin (reference encodings.py:151-199)."""
+    return _stack(xs, ys, ts, ps, B, device, sensor_size, True)
+
+
+def events_to_stack_no_polarity(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)):
+    """[B,H,W] signed counts per time bin (reference encodings.py:202-238)."""
+    return _stack(xs, ys, ts, ps, B, device, sensor_size, False)
+
+
+def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240), temporal_bilinear=True):
+    """Voxel grid without y-flip (reference encodings.py:100-148): bilinear in time, or hard bins
+    through the binary search when temporal_bilinear=False."""
+    if not temporal_bilinear:
+        return _stack(xs, ys, ts, ps, B, device, sensor_size, False)
+    if device is None:
+        device = xs.device
+    n = _chk(xs, ys, ts, ps)
+    eo = _early_out(ts, B, sensor_size, device)
+    if eo is not None:
+        return eo
+    assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
+    h, w = sensor_size
+    out = torch.empty(B, h, w, dtype=torch.float32, device=xs.device)
+    flags = _lib.ENC_TNORM | _MUT
+    out = _run(lambda *a: lib().bmc_encode_voxel(_p(xs), _p(ys), _p(ts), _p(ps), n, B, h, w, *a, flags,
+                                                 stream_ptr()), out)
+    return out.to(device)

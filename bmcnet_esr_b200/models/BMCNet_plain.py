@@ -1,0 +1,52 @@
+"""BMCNet_plain -- drop-in for the reference `models/BMCNet_plain.py` (:3-68).
+
+Same constructor, forward signature and state_dict keys (120, with the reference's aliasing);
+the forward pass is one call into libbmc_b200 (bmc_model_forward): NHWC bf16 tcgen05 kernels
+with fp32 accumulation, one CUDA graph per step.
+"""
+import torch
+import torch.nn as nn
+
+from ._engine import Engine
+from .submodules import BIE, PixelUnShuffle, initialize_weights
+from .._lib import MODEL_BMCNET_PLAIN
+
+
+class Backbone(nn.Module):
+    """Parameter container mirroring the reference Backbone (BMCNet_plain.py:3-22)."""
+
+    def __init__(self, n_c, n_b, scale, repeat):
+        super().__init__()
+        self.conv_f1 = nn.Conv2d(scale ** 2 + n_c + 2 * repeat, n_c, 3, 1, padding=(1, 1))
+        self.conv_f2 = self.conv_f1
+        self.conv_fs = nn.Conv2d(scale ** 2 * 2 + n_c + 2 * 2 * repeat, n_c, 3, 1, padding=(1, 1))
+        self.para_reschunk = nn.ModuleList([BIE(n_c)] * n_b)      # ONE block applied n_b times
+        self.scale = scale
+        self.conv_h = nn.Conv2d(n_c, n_c, 3, 1, padding=(1, 1))
+        self.conv_o = nn.Conv2d(n_c * 2, scale ** 2 * 2, 3, 1, padding=(1, 1))
+        # conv_fs keeps PyTorch's default init, as in the reference (BMCNet_plain.py:17)
+        initialize_weights([self.conv_f1, self.conv_f2, self.conv_h, self.conv_o], 0.1)
+
+
+class BMCNet_plain(nn.Module):
+    def __init__(self, scale, n_c, n_b, repeat=3):
+        super().__init__()
+        self.neuro = Backbone(n_c, n_b, scale, repeat=repeat)
+        self.scale = scale
+        self.down = PixelUnShuffle(scale)
+        self.repeat = repeat
+        self._engine = Engine(MODEL_BMCNET_PLAIN, scale, n_c, n_b, repeat)
+
+    def forward(self, x, x_h, x_o, init):
+        """x [B,2,T,H,W] counts (frames 0,1 used); x_h [B,n_c,H,W]; x_o [B,2*scale^2,H,W] when
+        `init` else the previous [B,2,sH,sW] output.  Returns (x_h, x_o) like the reference."""
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError('bmcnet_esr_b200 implements the inference path; call .eval() / no_grad')
+        with torch.no_grad():
+            (h,), o = self._engine.forward(self, x, [x_h], x_o, init)
+        return h, o
+
+    # device-resident recurrence for throughput (not part of the reference API)
+    def step(self, x, reset=False, want_output=True):
+        with torch.no_grad():
+            return self._engine.step(self, x, reset, want_output)

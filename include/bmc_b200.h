@@ -1,0 +1,216 @@
+/*
+ * bmc_b200.h -- C ABI of libbmc_b200.so: the B200 (sm_100a) implementation of the BMCNet
+ * inference hot path (event encoders + BMCNet / BMCNet_plain forward).
+ *
+ * The reference (Lqm26/BMCNet-ESR) is 100 % Python/PyTorch and has no FFI of its own
+ * (SURVEY.md section 8b): the interface a maintainer binds is its Python surface.  Each
+ * entry point below names the reference function it replaces (file:line under the
+ * reference root).  The Python mirror that calls these through ctypes lives in
+ * bmcnet_esr_b200/{dataloader/encodings.py,models/*.py}; INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C types only; every pointer marked "device" is a CUDA device pointer owned by
+ *     the caller (no allocation or ownership transfer across this ABI);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing syncs;
+ *   - return 0 on success, a negative bmc_status otherwise; bmc_last_error() gives the text
+ *     (thread-local);
+ *   - there is no CPU fallback: without a CUDA device every compute call fails with
+ *     BMC_ERR_CUDA.
+ */
+#ifndef BMC_B200_H_
+#define BMC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMC_ABI_VERSION 1
+
+typedef enum {
+    BMC_OK = 0,
+    BMC_ERR_ARG = -1,        /* bad argument (mirrors the reference's asserts, encodings.py:125,169,220,277,295) */
+    BMC_ERR_CUDA = -2,       /* CUDA runtime / driver error */
+    BMC_ERR_WORKSPACE = -3,  /* workspace missing or too small */
+    BMC_ERR_STATE = -4,      /* call order (weights not loaded, model not configured, ...) */
+    BMC_ERR_UNSUPPORTED = -5
+} bmc_status;
+
+int bmc_abi_version(void);
+const char* bmc_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Event encoders (reference: dataloader/encodings.py).
+ * Events are four device float32 arrays xs, ys, ts, ps of length n (base_dataset.py:24-31).
+ * Out-of-range events are zeroed IN PLACE in xs / ys (and ps where the reference does),
+ * exactly as the reference does (encodings.py:249-254, 34-39), when BMC_ENC_MUTATE is set.
+ * ---------------------------------------------------------------------------------------- */
+
+#define BMC_ENC_FLIP_Y 0x1u        /* y' = H-1-y (events_to_image family, encodings.py:265) */
+#define BMC_ENC_MUTATE 0x2u        /* reproduce the reference's in-place zeroing of out-of-range events */
+#define BMC_ENC_NO_QUIRKS 0x4u     /* drop the F9 leak of out-of-range events into pixel (0,0) */
+#define BMC_ENC_TNORM 0x8u         /* voxel: t = (ts-ts[0])/dt*(B-1) (encodings.py:127-129) instead of ts*(B-1) (:280) */
+#define BMC_ENC_BILINEAR 0x10u     /* image: spatial bilinear splat into (H+1)x(W+1) (encodings.py:57-65) */
+
+/* Scratch bytes needed by any encoder call below for an output of `out_elems` floats. */
+size_t bmc_encode_workspace_bytes(int64_t out_elems);
+
+/* events_to_channels (encodings.py:290-305): per-polarity counts, out = device float[2][H][W].
+ * Bit-exact for ps in {-1,0,+1}; other weights accumulate ps*ps in fp32 (order not fixed). */
+int bmc_encode_channels(float* xs, float* ys, const float* ps, int64_t n, int H, int W,
+                        float* out, void* workspace, size_t workspace_bytes, unsigned flags,
+                        void* stream);
+
+/* Batched form of the above for the dataloader pattern (h5dataset.py:308-309,526): window i
+ * covers events [offsets[i], offsets[i+1]) and fills out[i] = float[2][H][W]; `offsets` is a
+ * device int64[n_windows+1].  One CTA per window, no cross-window traffic. */
+int bmc_encode_channels_windows(float* xs, float* ys, const float* ps, const int64_t* offsets,
+                                int n_windows, int H, int W, float* out, unsigned flags,
+                                void* stream);
+
+/* events_to_image (encodings.py:241-269, with BMC_ENC_FLIP_Y) and events_to_image_torch
+ * (encodings.py:16-72, without; BMC_ENC_BILINEAR selects the padded bilinear splat whose
+ * output is float[H+1][W+1]).  Weighted fp32 scatter-add, out = device float[H][W]. */
+int bmc_encode_image(float* xs, float* ys, float* ps, int64_t n, int H, int W, float* out,
+                     void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
+
+/* events_to_voxel (encodings.py:272-287; FLIP_Y) and events_to_voxel_torch with
+ * temporal_bilinear=True (encodings.py:100-137; TNORM).  out = device float[bins][H][W]. */
+int bmc_encode_voxel(float* xs, float* ys, const float* ts, const float* ps, int64_t n, int bins,
+                     int H, int W, float* out, void* workspace, size_t workspace_bytes,
+                     unsigned flags, void* stream);
+
+/* events_to_stack_polarity (encodings.py:151-199; polarity=1, out = float[2][bins][H][W]),
+ * events_to_stack_no_polarity (encodings.py:202-238; polarity=0, out = float[bins][H][W]) and
+ * events_to_voxel_torch(temporal_bilinear=False) (encodings.py:138-145; same as polarity=0).
+ * The reference's float32 bin boundaries and its any-equal binary search (encodings.py:75-97)
+ * are evaluated on the device, so boundary events are double counted exactly as there.
+ * The reference's early-out (ts.sum()==0 or n<=3 -> zeros[bins][H][W]) is the CALLER's job
+ * (it changes the output shape); n <= 3 is rejected with BMC_ERR_ARG. */
+int bmc_encode_stack(float* xs, float* ys, const float* ts, float* ps, int64_t n, int bins,
+                     int H, int W, int polarity, float* out, void* workspace,
+                     size_t workspace_bytes, unsigned flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Model (reference: models/BMCNet.py, models/BMCNet_plain.py, models/submodules.py).
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct bmc_model bmc_model_t;
+
+#define BMC_MODEL_BMCNET 0        /* models/BMCNet.py:87-121 */
+#define BMC_MODEL_BMCNET_PLAIN 1  /* models/BMCNet_plain.py:36-68 */
+
+/* Constructor arguments of BMCNet(scale, n_c, n_b, repeat) (BMCNet.py:88).  The kernels are
+ * specialised for what every caller passes (infer_BMCNet.py:111, train.py:640): n_c = 128,
+ * scale = 4, repeat = 3; n_b is free.  Anything else returns NULL (see bmc_last_error). */
+bmc_model_t* bmc_model_create(int kind, int scale, int n_c, int n_b, int repeat);
+void bmc_model_destroy(bmc_model_t* m);
+
+/* Bytes of device memory the caller must provide for the repacked (bf16, K-major) weights. */
+size_t bmc_model_weight_bytes(const bmc_model_t* m);
+
+/* Load a reference-format state_dict (318 keys for BMCNet / 120 for plain; aliases allowed and
+ * expected to hold equal values).  `tensors[i]` is a device float32 pointer to the
+ * contiguous tensor named `names[i]` with `numels[i]` elements.  Missing or unexpected names
+ * fail like load_state_dict(strict=True) (infer_BMCNet.py:112).  The repacked copy is written
+ * to `weight_buf` (>= bmc_model_weight_bytes), which must stay alive until destroy/reload. */
+int bmc_model_load_state_dict(bmc_model_t* m, const char* const* names,
+                              const float* const* tensors, const int64_t* numels, int n_tensors,
+                              void* weight_buf, size_t weight_buf_bytes, void* stream);
+
+/* Fix the problem size (batch of independent sequences, LR height/width) and report the
+ * activation arena the caller must provide via bmc_model_bind_workspace. */
+int bmc_model_configure(bmc_model_t* m, int batch, int H, int W);
+size_t bmc_model_workspace_bytes(const bmc_model_t* m);
+int bmc_model_bind_workspace(bmc_model_t* m, void* workspace, size_t workspace_bytes);
+
+/* One recurrent step == one `forward` of the reference module.
+ *   x        device float32, logical shape [B,2,T,H,W] addressed through `x_strides` (elements);
+ *            frames t=0 and t=1 are used (BMCNet.py:106-107).  The reference caller passes a
+ *            transposed view (infer_BMCNet.py:50), hence the strides.
+ *   x_h*     device float32 [B,128,H,W] contiguous: hidden states in (x_h_p/x_h_n NULL for plain).
+ *   x_o      device float32: [B,32,H,W] when init != 0, else the previous output [B,2,4H,4W].
+ *   out_*    device float32 outputs, same shapes as the inputs; out_o is [B,2,4H,4W].
+ * Argument order and meaning follow BMCNet.forward (BMCNet.py:95) / BMCNet_plain.forward
+ * (BMCNet_plain.py:44), including the positional hand-over of the three hidden states into
+ * Backbone.forward (BMCNet.py:57 vs :115). */
+int bmc_model_forward(bmc_model_t* m, const float* x, const int64_t x_strides[5],
+                      const float* x_h, const float* x_h_p, const float* x_h_n, const float* x_o,
+                      int init, float* out_h, float* out_h_p, float* out_h_n, float* out_o,
+                      void* stream);
+
+/* Device-resident recurrence for throughput runs: identical arithmetic, but the hidden states
+ * and the fed-back prediction stay inside the workspace between steps (no fp32 NCHW round
+ * trip).  `reset` != 0 restarts from the zero state of infer_BMCNet.py:55-60 (init=True).
+ * out_o may be NULL to skip emitting the prediction. */
+int bmc_model_step(bmc_model_t* m, const float* x, const int64_t x_strides[5], int reset,
+                   float* out_o, void* stream);
+
+/* Number of kernels one forward/step enqueues (for bench.py's gpu_launches). */
+int bmc_model_launches_per_step(const bmc_model_t* m);
+
+/* 0 = tcgen05/TMA kernels (product), 1 = plain SIMT kernels of the same arithmetic, kept ON
+ * THE DEVICE as a debugging cross-check for the tensor-core path.  Never a CPU path. */
+int bmc_model_set_debug_simt(bmc_model_t* m, int enable);
+
+/* ------------------------------------------------------------------------------------------
+ * Per-kernel entry points for unit parity (SURVEY section 8b "bmc_conv3x3, bmc_bie").
+ * Activations are bf16 in the padded NHWC layout described in DESIGN.md:
+ *   rows = B * R, R = roundup((H+2)*(W+2), 128), row r of image b <-> padded pixel
+ *   (r / (W+2), r % (W+2)); halo and tail rows hold zeros.
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct {
+    /* A operand: up to 3 concatenated sources (torch.cat along channels, e.g. BMCNet.py:64) */
+    int n_seg;
+    const void* a[3];       /* device bf16 [a_rows][a_ch] */
+    int a_rows[3];
+    int a_ch[3];            /* multiple of 64 */
+    int a_row_base[3];      /* row of the source that pairs with output row 0 */
+    /* B operand: weights, device bf16 chunk-major [w_k/64][w_rows][64] */
+    const void* w;
+    int w_rows, w_k;
+    int w_row_base;         /* first of the N rows used */
+    int w_img_stride;       /* added per image (dynamic per-image weights, submodules.py:72-73) */
+    const float* bias;      /* device float[N] or NULL */
+    const void* residual;   /* device bf16 [.][N] added after activation, or NULL */
+    int res_row_base;
+    void* out_bf16;         /* device bf16 [.][N] or NULL */
+    int out_row_base;
+    float* out_f32;         /* device float [.][N] or NULL (same row base) */
+    int relu;
+    /* optional fused channel LayerNorm of (acc + bias) (submodules.py:127-139), N = 128 only */
+    const float* ln_gamma;  /* device float[N] or NULL */
+    const float* ln_beta;
+    float ln_eps;
+} bmc_gemm_job_t;
+
+/* Weights are chunk-major: w is bf16 [w_k/64][w_rows][64] (K index = (segment, tap, channel)).
+ * out[m, :] = act(LN?(sum_seg sum_tap A_seg[m + dy*(W+2) + dx, :] . W[:, seg, tap, :]^T + bias)) + res
+ * for all rows m of B images; n = 128 or 32 output channels; taps = 1 (1x1) or 9 (3x3, pad 1).
+ * All jobs of one call share the shape and run in one launch.  impl: 0 tcgen05, 1 SIMT debug. */
+int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, int n, int taps, int B, int H, int W,
+                  int impl, void* stream);
+
+/* att[b] = centres[b]^T . v[b] * scale over the pixels of image b (submodules.py:69-70), then
+ * row softmax (submodules.py:72-73) written as bf16 [B][128][128] "dynamic weights".
+ * centres, v: device bf16 [B*R][128]; partial: device float[B][n_split][128][128] scratch. */
+int bmc_attention_weights(const void* centres, const void* v, int B, int H, int W, float scale,
+                          float* partial, int n_split, void* probs_bf16, int impl, void* stream);
+
+/* Channel LayerNorm (submodules.py:127-139), bf16 [rows][128] -> bf16 [rows][128]. */
+int bmc_layernorm_rows(const void* in_bf16, const float* gamma, const float* beta, float eps,
+                       int64_t rows, void* out_bf16, void* stream);
+
+/* fp32 NCHW [B,C,H,W] <-> padded NHWC bf16 [B*R][c_pad] (channels [c_off, c_off+C)). */
+int bmc_pack_nchw(const float* src, int B, int C, int H, int W, void* dst_bf16, int c_pad,
+                  int c_off, void* stream);
+int bmc_unpack_nchw(const void* src_bf16, int B, int C, int H, int W, int c_pad, int c_off,
+                    float* dst, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMC_B200_H_ */
