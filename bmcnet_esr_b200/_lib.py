@@ -4,7 +4,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libbmc_b200.so')
+# BMC_B200_LIB selects another build (e.g. the bf16 variant made by `build.py --bf16`)
+LIB_PATH = os.environ.get('BMC_B200_LIB') or os.path.join(_HERE, 'libbmc_b200.so')
 
 ENC_FLIP_Y, ENC_MUTATE, ENC_NO_QUIRKS, ENC_TNORM, ENC_BILINEAR = 0x1, 0x2, 0x4, 0x8, 0x10
 MODEL_BMCNET, MODEL_BMCNET_PLAIN = 0, 1
@@ -16,7 +17,7 @@ class GemmJob(C.Structure):
     """bmc_gemm_job_t"""
     _fields_ = [('n_seg', _i), ('a', _vp * 3), ('a_rows', _i * 3), ('a_ch', _i * 3), ('a_row_base', _i * 3),
                 ('w', _vp), ('w_rows', _i), ('w_k', _i), ('w_row_base', _i), ('w_img_stride', _i),
-                ('bias', _vp), ('residual', _vp), ('res_row_base', _i), ('out_bf16', _vp),
+                ('bias', _vp), ('residual', _vp), ('res_row_base', _i), ('out_act16', _vp),
                 ('out_row_base', _i), ('out_f32', _vp), ('relu', _i),
                 ('ln_gamma', _vp), ('ln_beta', _vp), ('ln_eps', _f)]
 
@@ -25,6 +26,7 @@ class GemmJob(C.Structure):
 SIGNATURES = {
     'bmc_abi_version': (_i, []),
     'bmc_last_error': (C.c_char_p, []),
+    'bmc_act_dtype': (C.c_char_p, []),
     'bmc_encode_workspace_bytes': (_sz, [_i64]),
     'bmc_encode_channels': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_channels_windows': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _u, _vp]),
@@ -71,6 +73,12 @@ def lib():
             fn.argtypes = args
         _lib = l
     return _lib
+
+
+def act_dtype():
+    """torch dtype of the 16-bit activation / weight tensors of the loaded build."""
+    import torch
+    return {'f16': torch.float16, 'bf16': torch.bfloat16}[lib().bmc_act_dtype().decode()]
 
 
 def check(rc):

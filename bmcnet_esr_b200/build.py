@@ -32,9 +32,13 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=True):
-    """Compile every CUDA source to an object (in parallel) and link the shared library."""
-    objdir = os.path.join(HERE, 'build')
+def build(force=False, verbose=True, bf16=False):
+    """Compile every CUDA source to an object (in parallel) and link the shared library.
+    bf16=True builds the bf16-operand variant as libbmc_b200_bf16.so (select it at run time
+    with BMC_B200_LIB=<path>); the default library uses fp16 operands (Precision)."""
+    objdir = os.path.join(HERE, 'build', 'bf16' if bf16 else 'f16')
+    flags = NVCC_FLAGS + (['-DBMC_ACT_BF16'] if bf16 else [])
+    lib = LIB.replace('.so', '_bf16.so') if bf16 else LIB
     os.makedirs(objdir, exist_ok=True)
     hdrs = [os.path.join(CSRC, h) for h in HEADERS]
     procs, objs = [], []
@@ -43,7 +47,7 @@ def build(force=False, verbose=True):
         o = os.path.join(objdir, src.replace('.cu', '.o'))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            cmd = [_nvcc()] + NVCC_FLAGS + ['-c', s, '-o', o]
+            cmd = [_nvcc()] + flags + ['-c', s, '-o', o]
             if verbose:
                 print(' '.join(cmd), flush=True)
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -53,13 +57,13 @@ def build(force=False, verbose=True):
             raise RuntimeError('nvcc failed for %s:\n%s' % (src, out))
         if verbose and out.strip():
             print(out)
-    if force or procs or _stale(LIB, objs):
-        cmd = [_nvcc(), '-shared', '-o', LIB] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
+    if force or procs or _stale(lib, objs):
+        cmd = [_nvcc(), '-shared', '-o', lib] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a']
         if verbose:
             print(' '.join(cmd), flush=True)
         subprocess.check_call(cmd)
-    return LIB
+    return lib
 
 
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv))
+    print(build(force='--force' in sys.argv, bf16='--bf16' in sys.argv))

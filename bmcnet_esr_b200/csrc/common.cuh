@@ -14,6 +14,19 @@
 
 #define BMC_EXPORT __attribute__((visibility("default")))
 
+// 16-bit activation / weight type of the tensor-core path.  Default fp16 (11-bit significand):
+// measured against the reference fp32 forward, bf16 operands miss the max-abs 1e-2 bar on the
+// full BMCNet (1.2e-2) while fp16 holds it with margin (DESIGN.md "Precision").  Both feed the
+// same tcgen05 kind::f16 instruction at the same rate; -DBMC_ACT_BF16 selects bf16.
+#include <cuda_fp16.h>
+#ifdef BMC_ACT_BF16
+typedef __nv_bfloat16 act_t;
+#define BMC_ACT_NAME "bf16"
+#else
+typedef __half act_t;
+#define BMC_ACT_NAME "f16"
+#endif
+
 namespace bmc {
 
 // ---------------------------------------------------------------- errors
@@ -201,32 +214,54 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;
     return d;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): bf16 x bf16 -> fp32, M x N tile.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, bool a_mn_major,
+// Instruction descriptor (cute::UMMA::InstrDescriptor): act_t x act_t -> fp32, M x N tile.
+#ifdef BMC_ACT_BF16
+#define BMC_UMMA_FMT 1u                    // F16F32Format::BF16
+#else
+#define BMC_UMMA_FMT 0u                    // F16F32Format::F16
+#endif
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, bool a_mn_major,
                                                        bool b_mn_major) {
     return (1u << 4)                       // c_format  = F32
-           | (1u << 7)                     // a_format  = BF16
-           | (1u << 10)                    // b_format  = BF16
+           | (BMC_UMMA_FMT << 7)           // a_format
+           | (BMC_UMMA_FMT << 10)          // b_format
            | ((a_mn_major ? 1u : 0u) << 15)
            | ((b_mn_major ? 1u : 0u) << 16)
            | ((uint32_t)(N >> 3) << 17)
            | ((uint32_t)(M >> 4) << 24);
 }
 
-// ---------------------------------------------------------------- bf16 packing
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+// ---------------------------------------------------------------- 16-bit packing
+#ifdef BMC_ACT_BF16
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
-__device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
+__device__ __forceinline__ float2 unpack_act2(uint32_t u) {
     __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
     return __bfloat1622float2(v);
 }
+__device__ __forceinline__ act_t to_act(float f) { return __float2bfloat16(f); }
+__device__ __forceinline__ float from_act(act_t a) { return __bfloat162float(a); }
+#else
+// fp16 saturates at +-65504 instead of overflowing to inf
+__device__ __forceinline__ float sat_h(float f) { return fminf(fmaxf(f, -65504.f), 65504.f); }
+__device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
+    __half2 v = __floats2half2_rn(sat_h(lo), sat_h(hi));
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 unpack_act2(uint32_t u) {
+    __half2 v = *reinterpret_cast<__half2*>(&u);
+    return __half22float2(v);
+}
+__device__ __forceinline__ act_t to_act(float f) { return __float2half_rn(sat_h(f)); }
+__device__ __forceinline__ float from_act(act_t a) { return __half2float(a); }
+#endif
 #endif  // __CUDACC__
 
 // ---------------------------------------------------------------- host: TMA descriptors
-// 2-D bf16 row-major [rows][cols] tensor, box = [box_rows][box_cols], 128-byte swizzle.
-int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+// 2-D act_t row-major [rows][cols] tensor, box = [box_rows][box_cols], 128-byte swizzle.
+int make_tmap_2d_act(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint32_t box_rows, uint32_t box_cols);
 
 }  // namespace bmc

@@ -26,18 +26,18 @@ struct GemmJobDev {
     int a_map[kMaxSeg];        // index into GemmParams::maps
     int a_row_base[kMaxSeg];   // row of the source paired with output row 0
     int a_col_base[kMaxSeg];   // first channel used
-    const __nv_bfloat16* a_ptr[kMaxSeg];   // same sources as raw pointers (SIMT kernel)
+    const act_t* a_ptr[kMaxSeg];   // same sources as raw pointers (SIMT kernel)
     int a_ld[kMaxSeg];
     long a_rows[kMaxSeg];
     int w_map;
-    const __nv_bfloat16* w_ptr;
+    const act_t* w_ptr;
     int w_rows;                // rows per K chunk of the weight matrix behind w_map / w_ptr
     int w_row_base;
     int w_img_stride;
     const float* bias;
-    const __nv_bfloat16* residual;
+    const act_t* residual;
     long res_row_base;
-    __nv_bfloat16* out;
+    act_t* out;
     long out_row_base;
     float* out_f32;
     int relu;
@@ -68,7 +68,7 @@ constexpr int kMaxPairs = 4;
 struct alignas(64) AttParams {
     CUtensorMap map_c, map_v;              // box [64 pixel rows][64 channels] over [rows][128]
     long c_row_base[kMaxPairs], v_row_base[kMaxPairs];
-    const __nv_bfloat16* c_ptr; const __nv_bfloat16* v_ptr;   // raw bases (SIMT kernel)
+    const act_t* c_ptr; const act_t* v_ptr;   // raw bases (SIMT kernel)
     int n_pairs, n_split;
     int pix_per_split;                     // multiple of 64
     float scale;
@@ -79,7 +79,7 @@ struct alignas(64) AttParams {
 struct SoftmaxParams {
     const float* partial;                  // as above
     int n_pairs, n_split, B;
-    __nv_bfloat16* w_base;                 // [rows][64] dynamic-weight arena; P of (pair, b) is the
+    act_t* w_base;                 // [rows][64] dynamic-weight arena; P of (pair, b) is the
     int w_row_base[kMaxPairs];             // chunk-major block [2][128][64] starting at row
     int w_img_stride;                      // w_row_base[pair] + b * w_img_stride
 };
@@ -90,18 +90,19 @@ int launch_att(const AttParams& p, int impl, cudaStream_t st);
 int launch_att_softmax(const SoftmaxParams& p, cudaStream_t st);
 
 // Pointwise kernels (pointwise.cu)
-int launch_layernorm(const __nv_bfloat16* in, const float* gamma, const float* beta, float eps,
-                     long rows, __nv_bfloat16* out, cudaStream_t st);
-int launch_pack_nchw(const float* src, Geom g, int C, __nv_bfloat16* dst, int c_pad, int c_off,
+int launch_layernorm(const act_t* in, const float* gamma, const float* beta, float eps,
+                     long rows, act_t* out, cudaStream_t st);
+int launch_pack_nchw(const float* src, Geom g, int C, act_t* dst, int c_pad, int c_off,
                      cudaStream_t st);
-int launch_unpack_nchw(const __nv_bfloat16* src, Geom g, int C, int c_pad, int c_off, float* dst,
+int launch_unpack_nchw(const act_t* src, Geom g, int C, int c_pad, int c_off, float* dst,
                        cudaStream_t st);
+int launch_unpack_nchw_f32(const float* src, Geom g, int C, int c_pad, float* dst, cudaStream_t st);
 struct PackInputsParams {
     const float* x; long xs[5];            // [B,2,T,H,W] element strides
     const float* x_o;                      // [B,32,H,W] (init) or [B,2,4H,4W]; NULL = keep the o part
                                            // already in `mi` (or zero it when init)
     int init;
-    __nv_bfloat16* mi;                     // [B*R][64]
+    act_t* mi;                     // [B*R][64]
     Geom g;
 };
 int launch_pack_inputs(const PackInputsParams& p, cudaStream_t st);
@@ -109,12 +110,12 @@ struct EmitParams {
     const float* a;                        // conv_o result, fp32 [B*R][32]
     const float* x; long xs[5];            // f2 = x[:, :, 1]
     float* out_o;                          // [B,2,4H,4W] or NULL
-    __nv_bfloat16* mi_next;                // o part of the next step's input tensor, or NULL
+    act_t* mi_next;                // o part of the next step's input tensor, or NULL
     Geom g;
 };
 int launch_emit(const EmitParams& p, cudaStream_t st);
 int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out,
-                         int n_out_pad, int K, __nv_bfloat16* dst, int w_rows, int w_row_base,
+                         int n_out_pad, int K, act_t* dst, int w_rows, int w_row_base,
                          cudaStream_t st);
 
 }  // namespace bmc

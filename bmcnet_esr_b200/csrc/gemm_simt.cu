@@ -26,9 +26,9 @@ __global__ void conv_gemm_simt(const __grid_constant__ GemmParams p) {
             const bool in = arow >= 0 && arow < job.a_rows[s];
             for (int c = 0; c < p.chunks[s]; ++c, ++kchunk) {
                 if (!in || !valid) continue;
-                const __nv_bfloat16* a = job.a_ptr[s] + arow * job.a_ld[s] + job.a_col_base[s] + c * kChunkK;
-                const __nv_bfloat16* w = job.w_ptr + ((long)kchunk * job.w_rows + w_row) * kChunkK;
-                for (int k = 0; k < kChunkK; ++k) acc += __bfloat162float(a[k]) * __bfloat162float(w[k]);
+                const act_t* a = job.a_ptr[s] + arow * job.a_ld[s] + job.a_col_base[s] + c * kChunkK;
+                const act_t* w = job.w_ptr + ((long)kchunk * job.w_rows + w_row) * kChunkK;
+                for (int k = 0; k < kChunkK; ++k) acc += from_act(a[k]) * from_act(w[k]);
             }
         }
     }
@@ -45,9 +45,9 @@ __global__ void conv_gemm_simt(const __grid_constant__ GemmParams p) {
         acc = job.ln_gamma[n] * ((acc - mu) / sqrtf(var + job.ln_eps)) + job.ln_beta[n];
     }
     if (job.relu) acc = fmaxf(acc, 0.f);
-    if (job.residual && valid) acc += __bfloat162float(job.residual[(job.res_row_base + m) * N + n]);
+    if (job.residual && valid) acc += from_act(job.residual[(job.res_row_base + m) * N + n]);
     if (!valid) acc = 0.f;
-    if (job.out) job.out[(job.out_row_base + m) * N + n] = __float2bfloat16(acc);
+    if (job.out) job.out[(job.out_row_base + m) * N + n] = to_act(acc);
     if (job.out_f32) job.out_f32[(job.out_row_base + m) * N + n] = acc;
 }
 
@@ -64,11 +64,11 @@ __global__ void att_simt(const __grid_constant__ AttParams p) {
     const int pair = (int)(rest / p.g.B);
     const int pix0 = split * p.pix_per_split;
     const int pix1 = min(pix0 + p.pix_per_split, p.g.R);
-    const __nv_bfloat16* c = p.c_ptr + (p.c_row_base[pair] + (long)b * p.g.R) * 128;
-    const __nv_bfloat16* v = p.v_ptr + (p.v_row_base[pair] + (long)b * p.g.R) * 128;
+    const act_t* c = p.c_ptr + (p.c_row_base[pair] + (long)b * p.g.R) * 128;
+    const act_t* v = p.v_ptr + (p.v_row_base[pair] + (long)b * p.g.R) * 128;
     float acc = 0.f;
     for (int px = pix0; px < pix1; ++px)
-        acc += __bfloat162float(c[(long)px * 128 + c1]) * __bfloat162float(v[(long)px * 128 + c2]);
+        acc += from_act(c[(long)px * 128 + c1]) * from_act(v[(long)px * 128 + c2]);
     p.partial[idx] = acc * p.scale;
 }
 
@@ -96,10 +96,10 @@ __global__ void att_softmax(const SoftmaxParams p) {
     const float inv = 1.f / sum;
     const int col = lane * 4;                      // c' ; K chunk = col / 64
     const long row = p.w_row_base[pair] + (long)b * p.w_img_stride + (col >> 6) * 128 + c;
-    __nv_bfloat16* dst = p.w_base + row * kChunkK + (col & 63);
+    act_t* dst = p.w_base + row * kChunkK + (col & 63);
     uint2 o2;
-    o2.x = pack_bf16x2(a.x * inv, a.y * inv);
-    o2.y = pack_bf16x2(a.z * inv, a.w * inv);
+    o2.x = pack_act2(a.x * inv, a.y * inv);
+    o2.y = pack_act2(a.z * inv, a.w * inv);
     *reinterpret_cast<uint2*>(dst) = o2;
 }
 

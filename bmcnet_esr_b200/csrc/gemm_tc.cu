@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant
     } else if (warp == 1) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kTileM, N, false, false);
+            constexpr uint32_t idesc = umma_idesc_f16(kTileM, N, false, false);
             for (int it = 0; it < iters; ++it) {
                 const int st = it % STAGES;
                 mbar_wait(&full_bar[st], (it / STAGES) & 1);
@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant
         const bool valid = p.g.interior(r_img, y, x);
         mbar_wait(&acc_bar, 0);
         tc_fence_after_sync();
-        const __nv_bfloat16* res = job.residual ? job.residual + (job.res_row_base + m) * N : nullptr;
-        __nv_bfloat16* out = job.out ? job.out + (job.out_row_base + m) * N : nullptr;
+        const act_t* res = job.residual ? job.residual + (job.res_row_base + m) * N : nullptr;
+        act_t* out = job.out ? job.out + (job.out_row_base + m) * N : nullptr;
         float* outf = job.out_f32 ? job.out_f32 + (job.out_row_base + m) * N : nullptr;
         const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
         // Fused channel LayerNorm: this thread owns the whole row, so mean / variance are
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant
                     const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const float2 t = unpack_bf16x2(w[e]);
+                        const float2 t = unpack_act2(w[e]);
                         f[u * 8 + e * 2] += t.x;
                         f[u * 8 + e * 2 + 1] += t.y;
                     }
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant
                 uint4* op = reinterpret_cast<uint4*>(out + c * 32);
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
-                    op[u] = make_uint4(pack_bf16x2(f[u * 8], f[u * 8 + 1]), pack_bf16x2(f[u * 8 + 2], f[u * 8 + 3]),
-                                       pack_bf16x2(f[u * 8 + 4], f[u * 8 + 5]), pack_bf16x2(f[u * 8 + 6], f[u * 8 + 7]));
+                    op[u] = make_uint4(pack_act2(f[u * 8], f[u * 8 + 1]), pack_act2(f[u * 8 + 2], f[u * 8 + 3]),
+                                       pack_act2(f[u * 8 + 4], f[u * 8 + 5]), pack_act2(f[u * 8 + 6], f[u * 8 + 7]));
             }
             if (outf) {
                 float4* op = reinterpret_cast<float4*>(outf + c * 32);
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(kThreadsTc) att_tc(const __grid_constant__ Att
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 128, true, true);
+            constexpr uint32_t idesc = umma_idesc_f16(128, 128, true, true);
             for (int it = 0; it < iters; ++it) {
                 const int st = it % kAttStages;
                 mbar_wait(&full_bar[st], (it / kAttStages) & 1);

@@ -128,6 +128,7 @@ struct JobSpec {
     int res_slot = -1;
     int out_slot = -1;
     bool out_f32 = false;    // conv_o: fp32 [rows][32] side buffer
+    int hid32 = -1;          // hidden-state convs: also keep an fp32 copy [rows][128] (forward() output)
     int ln = -1;
 };
 
@@ -148,7 +149,7 @@ struct bmc_model {
     int w_rows_total = 0;
     size_t f32_floats = 0, kmap_ints = 0;
     // device weights
-    __nv_bfloat16* w_dev = nullptr;
+    act_t* w_dev = nullptr;
     float* f32_dev = nullptr;
     int* kmap_dev = nullptr;
     bool loaded = false;
@@ -157,7 +158,7 @@ struct bmc_model {
     Geom g;
     int n_slots = 0, n_split = 1, pix_per_split = 0;
     size_t ws_bytes = 0;
-    size_t off_mi = 0, off_a32 = 0, off_p = 0, off_partial = 0;
+    size_t off_mi = 0, off_a32 = 0, off_p = 0, off_partial = 0, off_hid32 = 0;
     char* ws = nullptr;
     CUtensorMap map_act, map_att, map_mi, map_w128, map_w32, map_p;
     // plan
@@ -175,11 +176,12 @@ struct bmc_model {
     int eager_runs = 0;
     bool use_graph = true;
 
-    __nv_bfloat16* slot_ptr(int s) const { return reinterpret_cast<__nv_bfloat16*>(ws) + (size_t)s * g.rows() * 128; }
-    __nv_bfloat16* mi_ptr() const { return reinterpret_cast<__nv_bfloat16*>(ws + off_mi); }
+    act_t* slot_ptr(int s) const { return reinterpret_cast<act_t*>(ws) + (size_t)s * g.rows() * 128; }
+    act_t* mi_ptr() const { return reinterpret_cast<act_t*>(ws + off_mi); }
     float* a32_ptr() const { return reinterpret_cast<float*>(ws + off_a32); }
-    __nv_bfloat16* p_ptr() const { return reinterpret_cast<__nv_bfloat16*>(ws + off_p); }
+    act_t* p_ptr() const { return reinterpret_cast<act_t*>(ws + off_p); }
     float* partial_ptr() const { return reinterpret_cast<float*>(ws + off_partial); }
+    float* hid32_ptr(int i) const { return reinterpret_cast<float*>(ws + off_hid32) + (size_t)i * g.rows() * 128; }
 };
 
 namespace {
@@ -319,7 +321,7 @@ struct Builder {
             d.res_row_base = 0;
             d.out = js.out_slot >= 0 ? m->slot_ptr(js.out_slot) : nullptr;
             d.out_row_base = 0;
-            d.out_f32 = js.out_f32 ? m->a32_ptr() : nullptr;
+            d.out_f32 = js.out_f32 ? m->a32_ptr() : (js.hid32 >= 0 ? m->hid32_ptr(js.hid32) : nullptr);
             if (js.ln >= 0) {
                 d.ln_gamma = m->f32_dev + m->lns[js.ln].gamma_off;
                 d.ln_beta = m->f32_dev + m->lns[js.ln].beta_off;
@@ -442,7 +444,7 @@ struct Builder {
             x1 = o[0].x1; x2 = o[0].x2; xs = o[0].xs;
         }
         // x_h = relu(conv_h(xs)) written in place of the consumed hidden state; x_o = conv_o(cat[x1,x2])
-        JobSpec jh; jh.segs = {{0, xs}}; jh.weight = W("h"); jh.relu = true; jh.out_slot = H;
+        JobSpec jh; jh.segs = {{0, xs}}; jh.weight = W("h"); jh.relu = true; jh.out_slot = H; jh.hid32 = 0;
         gemm({jh}, 128, 9);
         JobSpec jo; jo.segs = {{0, x1}, {0, x2}}; jo.weight = W("o"); jo.out_f32 = true;
         gemm({jo}, 32, 9);
@@ -501,6 +503,7 @@ struct Builder {
         const char* hn[3] = {"conv_hs", "conv_hp", "conv_hn"};
         for (int j = 0; j < 3; ++j) {
             jobs[j].segs = {{0, hin[j]}}; jobs[j].weight = W(hn[j]); jobs[j].relu = true; jobs[j].out_slot = m->slot_h[j];
+            jobs[j].hid32 = j;
         }
         gemm(jobs, 128, 9);
         JobSpec jo; jo.segs = {{0, xp_s}, {0, xn_s}}; jo.weight = W("o"); jo.out_f32 = true;
@@ -616,7 +619,7 @@ extern "C" BMC_EXPORT int bmc_model_load_state_dict(bmc_model_t* m, const char* 
         return BMC_OK;
     };
     char* base = static_cast<char*>(weight_buf);
-    m->w_dev = reinterpret_cast<__nv_bfloat16*>(base);
+    m->w_dev = reinterpret_cast<act_t*>(base);
     m->f32_dev = reinterpret_cast<float*>(base + align_up((size_t)m->w_rows_total * 128, 1024));
     m->kmap_dev = reinterpret_cast<int*>(reinterpret_cast<char*>(m->f32_dev) + align_up(m->f32_floats * 4, 1024));
     BMC_CUDA(cudaMemsetAsync(m->f32_dev, 0, m->f32_floats * 4, st));
@@ -653,9 +656,9 @@ extern "C" BMC_EXPORT int bmc_model_load_state_dict(bmc_model_t* m, const char* 
         BMC_CUDA(cudaMemcpyAsync(m->f32_dev + ln.gamma_off, g, 512, cudaMemcpyDeviceToDevice, st));
         BMC_CUDA(cudaMemcpyAsync(m->f32_dev + ln.beta_off, b, 512, cudaMemcpyDeviceToDevice, st));
     }
-    int rc = make_tmap_2d_bf16(&m->map_w128, m->w_dev, (uint64_t)m->w_rows_total, 64, 128, 64);
+    int rc = make_tmap_2d_act(&m->map_w128, m->w_dev, (uint64_t)m->w_rows_total, 64, 128, 64);
     if (rc) return rc;
-    rc = make_tmap_2d_bf16(&m->map_w32, m->w_dev, (uint64_t)m->w_rows_total, 64, 32, 64);
+    rc = make_tmap_2d_act(&m->map_w32, m->w_dev, (uint64_t)m->w_rows_total, 64, 32, 64);
     if (rc) return rc;
     m->loaded = true;
     if (m->bound) {            // weights moved: rebuild the plan against the new pointers
@@ -689,6 +692,7 @@ extern "C" BMC_EXPORT int bmc_model_configure(bmc_model_t* m, int batch, int H, 
     m->off_a32 = off; off += align_up(rows * 128, 1024);
     m->off_p = off; off += align_up((size_t)kMaxPairs * batch * 256 * 128, 1024);
     m->off_partial = off; off += align_up((size_t)kMaxPairs * batch * m->n_split * 128 * 128 * 4, 1024);
+    m->off_hid32 = off; off += align_up((size_t)(m->kind == BMC_MODEL_BMCNET ? 3 : 1) * rows * 512, 1024);
     m->ws_bytes = off;
     m->configured = true;
     return BMC_OK;
@@ -709,10 +713,10 @@ extern "C" BMC_EXPORT int bmc_model_bind_workspace(bmc_model_t* m, void* workspa
     // halo / tail rows must be zero and are never written with anything else afterwards
     BMC_CUDA(cudaMemset(m->ws, 0, m->ws_bytes));
     const uint64_t rows = (uint64_t)m->g.rows();
-    int rc = make_tmap_2d_bf16(&m->map_act, m->slot_ptr(0), rows * m->n_slots, 128, 128, 64);
-    if (!rc) rc = make_tmap_2d_bf16(&m->map_att, m->slot_ptr(0), rows * m->n_slots, 128, 64, 64);
-    if (!rc) rc = make_tmap_2d_bf16(&m->map_mi, m->mi_ptr(), rows, 64, 128, 64);
-    if (!rc) rc = make_tmap_2d_bf16(&m->map_p, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128, 64);
+    int rc = make_tmap_2d_act(&m->map_act, m->slot_ptr(0), rows * m->n_slots, 128, 128, 64);
+    if (!rc) rc = make_tmap_2d_act(&m->map_att, m->slot_ptr(0), rows * m->n_slots, 128, 64, 64);
+    if (!rc) rc = make_tmap_2d_act(&m->map_mi, m->mi_ptr(), rows, 64, 128, 64);
+    if (!rc) rc = make_tmap_2d_act(&m->map_p, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128, 64);
     if (rc) return rc;
     m->dry = false;
     Builder b{m};
@@ -760,7 +764,7 @@ extern "C" BMC_EXPORT int bmc_model_forward(bmc_model_t* m, const float* x, cons
     rc = run_plan(m, st);
     if (rc) return rc;
     for (int i = 0; i < nh; ++i) {
-        rc = launch_unpack_nchw(m->slot_ptr(m->slot_h[i]), m->g, 128, 128, 0, hout[i], st);
+        rc = launch_unpack_nchw_f32(m->hid32_ptr(i), m->g, 128, 128, hout[i], st);   // fp32 accumulators, not the 16-bit copy
         if (rc) return rc;
     }
     EmitParams ep;
@@ -812,7 +816,7 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
         for (size_t i = 0; i < map_key.size(); ++i)
             if (map_key[i] == ptr) { *idx = (int)i; return BMC_OK; }
         BMC_REQUIRE(n_maps < kMaxMaps, "conv_gemm: more than %d distinct operand tensors in one call", kMaxMaps);
-        int rc = impl == 0 ? make_tmap_2d_bf16(&p.maps[n_maps], ptr, rows, cols, box_rows, 64) : BMC_OK;
+        int rc = impl == 0 ? make_tmap_2d_act(&p.maps[n_maps], ptr, rows, cols, box_rows, 64) : BMC_OK;
         if (rc) return rc;
         map_key.push_back(ptr);
         *idx = n_maps++;
@@ -828,35 +832,35 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
             int rc = get_map(js.a[s], (uint64_t)js.a_rows[s], (uint64_t)js.a_ch[s], 128, &d.a_map[s]);
             if (rc) return rc;
             d.a_row_base[s] = js.a_row_base[s]; d.a_col_base[s] = 0;
-            d.a_ptr[s] = static_cast<const __nv_bfloat16*>(js.a[s]); d.a_ld[s] = js.a_ch[s]; d.a_rows[s] = js.a_rows[s];
+            d.a_ptr[s] = static_cast<const act_t*>(js.a[s]); d.a_ld[s] = js.a_ch[s]; d.a_rows[s] = js.a_rows[s];
             kch += p.chunks[s] * taps;
         }
         BMC_REQUIRE(js.w && js.w_k == kch * 64, "conv_gemm: weight K (%d) != %d", js.w_k, kch * 64);
         const uint64_t w_total = (uint64_t)js.w_row_base + (uint64_t)(B - 1) * js.w_img_stride + (uint64_t)js.w_rows * kch;
         int rc = get_map(js.w, w_total, 64, (uint32_t)n, &d.w_map);
         if (rc) return rc;
-        d.w_ptr = static_cast<const __nv_bfloat16*>(js.w); d.w_rows = js.w_rows;
+        d.w_ptr = static_cast<const act_t*>(js.w); d.w_rows = js.w_rows;
         d.w_row_base = js.w_row_base; d.w_img_stride = js.w_img_stride;
         d.bias = js.bias; d.relu = js.relu;
-        d.residual = static_cast<const __nv_bfloat16*>(js.residual); d.res_row_base = js.res_row_base;
-        d.out = static_cast<__nv_bfloat16*>(js.out_bf16); d.out_row_base = js.out_row_base; d.out_f32 = js.out_f32;
+        d.residual = static_cast<const act_t*>(js.residual); d.res_row_base = js.res_row_base;
+        d.out = static_cast<act_t*>(js.out_act16); d.out_row_base = js.out_row_base; d.out_f32 = js.out_f32;
         d.ln_gamma = js.ln_gamma; d.ln_beta = js.ln_beta; d.ln_eps = js.ln_eps;
     }
     return launch_conv_gemm(p, impl, as_stream(stream));
 }
 
 extern "C" BMC_EXPORT int bmc_attention_weights(const void* centres, const void* v, int B, int H, int W, float scale,
-                                     float* partial, int n_split, void* probs_bf16, int impl, void* stream) {
-    BMC_REQUIRE(centres && v && partial && probs_bf16 && n_split >= 1, "attention_weights: bad argument");
+                                     float* partial, int n_split, void* probs_act16, int impl, void* stream) {
+    BMC_REQUIRE(centres && v && partial && probs_act16 && n_split >= 1, "attention_weights: bad argument");
     const Geom g = Geom::make(B, H, W);
     AttParams a;
     memset(&a, 0, sizeof(a));
     if (impl == 0) {
-        int rc = make_tmap_2d_bf16(&a.map_c, centres, (uint64_t)g.rows(), 128, 64, 64);
-        if (!rc) rc = make_tmap_2d_bf16(&a.map_v, v, (uint64_t)g.rows(), 128, 64, 64);
+        int rc = make_tmap_2d_act(&a.map_c, centres, (uint64_t)g.rows(), 128, 64, 64);
+        if (!rc) rc = make_tmap_2d_act(&a.map_v, v, (uint64_t)g.rows(), 128, 64, 64);
         if (rc) return rc;
     }
-    a.c_ptr = static_cast<const __nv_bfloat16*>(centres); a.v_ptr = static_cast<const __nv_bfloat16*>(v);
+    a.c_ptr = static_cast<const act_t*>(centres); a.v_ptr = static_cast<const act_t*>(v);
     a.n_pairs = 1; a.n_split = n_split;
     a.pix_per_split = ((g.R / 64 + n_split - 1) / n_split) * 64;
     a.scale = scale; a.partial = partial; a.g = g;
@@ -865,25 +869,25 @@ extern "C" BMC_EXPORT int bmc_attention_weights(const void* centres, const void*
     SoftmaxParams s;
     memset(&s, 0, sizeof(s));
     s.partial = partial; s.n_pairs = 1; s.n_split = n_split; s.B = B;
-    s.w_base = static_cast<__nv_bfloat16*>(probs_bf16); s.w_img_stride = 256;
+    s.w_base = static_cast<act_t*>(probs_act16); s.w_img_stride = 256;
     return launch_att_softmax(s, as_stream(stream));
 }
 
-extern "C" BMC_EXPORT int bmc_layernorm_rows(const void* in_bf16, const float* gamma, const float* beta, float eps, int64_t rows,
-                                  void* out_bf16, void* stream) {
-    BMC_REQUIRE(in_bf16 && gamma && beta && out_bf16 && rows >= 0, "layernorm_rows: bad argument");
-    return launch_layernorm(static_cast<const __nv_bfloat16*>(in_bf16), gamma, beta, eps, rows,
-                            static_cast<__nv_bfloat16*>(out_bf16), as_stream(stream));
+extern "C" BMC_EXPORT int bmc_layernorm_rows(const void* in_act16, const float* gamma, const float* beta, float eps, int64_t rows,
+                                  void* out_act16, void* stream) {
+    BMC_REQUIRE(in_act16 && gamma && beta && out_act16 && rows >= 0, "layernorm_rows: bad argument");
+    return launch_layernorm(static_cast<const act_t*>(in_act16), gamma, beta, eps, rows,
+                            static_cast<act_t*>(out_act16), as_stream(stream));
 }
 
-extern "C" BMC_EXPORT int bmc_pack_nchw(const float* src, int B, int C, int H, int W, void* dst_bf16, int c_pad, int c_off,
+extern "C" BMC_EXPORT int bmc_pack_nchw(const float* src, int B, int C, int H, int W, void* dst_act16, int c_pad, int c_off,
                              void* stream) {
-    BMC_REQUIRE(src && dst_bf16 && C >= 1 && c_off >= 0 && c_off + C <= c_pad, "pack_nchw: bad argument");
-    return launch_pack_nchw(src, Geom::make(B, H, W), C, static_cast<__nv_bfloat16*>(dst_bf16), c_pad, c_off, as_stream(stream));
+    BMC_REQUIRE(src && dst_act16 && C >= 1 && c_off >= 0 && c_off + C <= c_pad, "pack_nchw: bad argument");
+    return launch_pack_nchw(src, Geom::make(B, H, W), C, static_cast<act_t*>(dst_act16), c_pad, c_off, as_stream(stream));
 }
 
-extern "C" BMC_EXPORT int bmc_unpack_nchw(const void* src_bf16, int B, int C, int H, int W, int c_pad, int c_off, float* dst,
+extern "C" BMC_EXPORT int bmc_unpack_nchw(const void* src_act16, int B, int C, int H, int W, int c_pad, int c_off, float* dst,
                                void* stream) {
-    BMC_REQUIRE(src_bf16 && dst && C >= 1 && c_off >= 0 && c_off + C <= c_pad, "unpack_nchw: bad argument");
-    return launch_unpack_nchw(static_cast<const __nv_bfloat16*>(src_bf16), Geom::make(B, H, W), C, c_pad, c_off, dst, as_stream(stream));
+    BMC_REQUIRE(src_act16 && dst && C >= 1 && c_off >= 0 && c_off + C <= c_pad, "unpack_nchw: bad argument");
+    return launch_unpack_nchw(static_cast<const act_t*>(src_act16), Geom::make(B, H, W), C, c_pad, c_off, dst, as_stream(stream));
 }

@@ -7,14 +7,14 @@ namespace {
 
 // ---------------------------------------------------------------- LayerNorm over 128 channels
 // submodules.py:127-139: mu, biased var, (x-mu)/sqrt(var+eps)*w+b.  One warp per row, 4 ch / lane.
-__global__ void layernorm_rows(const __nv_bfloat16* __restrict__ in, const float* __restrict__ gamma,
+__global__ void layernorm_rows(const act_t* __restrict__ in, const float* __restrict__ gamma,
                                const float* __restrict__ beta, float eps, long rows,
-                               __nv_bfloat16* __restrict__ out) {
+                               act_t* __restrict__ out) {
     const long row = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     const uint2 raw = *reinterpret_cast<const uint2*>(in + row * 128 + lane * 4);
-    const float2 a = unpack_bf16x2(raw.x), b = unpack_bf16x2(raw.y);
+    const float2 a = unpack_act2(raw.x), b = unpack_act2(raw.y);
     float s = a.x + a.y + b.x + b.y;
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mu = s * (1.f / 128.f);
@@ -25,14 +25,14 @@ __global__ void layernorm_rows(const __nv_bfloat16* __restrict__ in, const float
     const float4 g = *reinterpret_cast<const float4*>(gamma + lane * 4);
     const float4 bt = *reinterpret_cast<const float4*>(beta + lane * 4);
     uint2 o2;
-    o2.x = pack_bf16x2(g.x * (d0 * rstd) + bt.x, g.y * (d1 * rstd) + bt.y);
-    o2.y = pack_bf16x2(g.z * (d2 * rstd) + bt.z, g.w * (d3 * rstd) + bt.w);
+    o2.x = pack_act2(g.x * (d0 * rstd) + bt.x, g.y * (d1 * rstd) + bt.y);
+    o2.y = pack_act2(g.z * (d2 * rstd) + bt.z, g.w * (d3 * rstd) + bt.w);
     *reinterpret_cast<uint2*>(out + row * 128 + lane * 4) = o2;
 }
 
 // ---------------------------------------------------------------- NCHW fp32 -> padded NHWC bf16
 // thread = (pixel, 8-channel group); lanes run over pixels so the NCHW reads coalesce.
-__global__ void pack_nchw(const float* __restrict__ src, Geom g, int C, __nv_bfloat16* __restrict__ dst,
+__global__ void pack_nchw(const float* __restrict__ src, Geom g, int C, act_t* __restrict__ dst,
                           int c_pad, int c_off) {
     const int HW = g.H * g.W;
     const int groups = (C + 7) / 8;
@@ -49,16 +49,16 @@ __global__ void pack_nchw(const float* __restrict__ src, Geom g, int C, __nv_bfl
     float f[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) f[j] = (grp * 8 + j < C) ? s[(long)j * HW] : 0.f;
-    __nv_bfloat16* d = dst + row * c_pad + c_off + grp * 8;
+    act_t* d = dst + row * c_pad + c_off + grp * 8;
     if (grp * 8 + 8 <= C && ((c_off & 7) == 0)) {
-        *reinterpret_cast<uint4*>(d) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                  pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+        *reinterpret_cast<uint4*>(d) = make_uint4(pack_act2(f[0], f[1]), pack_act2(f[2], f[3]),
+                                                  pack_act2(f[4], f[5]), pack_act2(f[6], f[7]));
     } else {
-        for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[j] = __float2bfloat16(f[j]);
+        for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[j] = to_act(f[j]);
     }
 }
 
-__global__ void unpack_nchw(const __nv_bfloat16* __restrict__ src, Geom g, int C, int c_pad, int c_off,
+__global__ void unpack_nchw(const act_t* __restrict__ src, Geom g, int C, int c_pad, int c_off,
                             float* __restrict__ dst) {
     const int HW = g.H * g.W;
     const int groups = (C + 7) / 8;
@@ -71,9 +71,26 @@ __global__ void unpack_nchw(const __nv_bfloat16* __restrict__ src, Geom g, int C
     const int pix = (int)(r - (long)grp * HW);
     const int y = pix / g.W, x = pix - y * g.W;
     const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
-    const __nv_bfloat16* s = src + row * c_pad + c_off + grp * 8;
+    const act_t* s = src + row * c_pad + c_off + grp * 8;
     float* d = dst + ((long)b * C + grp * 8) * HW + pix;
-    for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[(long)j * HW] = __bfloat162float(s[j]);
+    for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[(long)j * HW] = from_act(s[j]);
+}
+
+__global__ void unpack_nchw_f32(const float* __restrict__ src, Geom g, int C, int c_pad, float* __restrict__ dst) {
+    const int HW = g.H * g.W;
+    const int groups = (C + 7) / 8;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long per_img = (long)HW * groups;
+    if (idx >= per_img * g.B) return;
+    const int b = (int)(idx / per_img);
+    const long r = idx - (long)b * per_img;
+    const int grp = (int)(r / HW);
+    const int pix = (int)(r - (long)grp * HW);
+    const int y = pix / g.W, x = pix - y * g.W;
+    const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
+    const float* s = src + row * c_pad + grp * 8;
+    float* d = dst + ((long)b * C + grp * 8) * HW + pix;
+    for (int j = 0; j < 8 && grp * 8 + j < C; ++j) d[(long)j * HW] = s[j];
 }
 
 // ---------------------------------------------------------------- per-step input tensor "MI"
@@ -91,15 +108,15 @@ __global__ void pack_inputs(PackInputsParams p) {
     const int b = (int)(idx / HW);
     const int pix = (int)(idx - (long)b * HW);
     const int y = pix / g.W, x = pix - y * g.W;
-    __nv_bfloat16* d = p.mi + ((long)b * g.R + (long)(y + 1) * g.Wp + (x + 1)) * 64;
+    act_t* d = p.mi + ((long)b * g.R + (long)(y + 1) * g.Wp + (x + 1)) * 64;
     const float* xb = p.x + b * p.xs[0] + y * p.xs[3] + x * p.xs[4];
     const float f1p = xb[0], f2p = xb[p.xs[2]];
     const float f1n = xb[p.xs[1]], f2n = xb[p.xs[1] + p.xs[2]];
-    const uint32_t w1p = pack_bf16x2(f1p, f1p), w2p = pack_bf16x2(f2p, f2p);
-    const uint32_t w1n = pack_bf16x2(f1n, f1n), w2n = pack_bf16x2(f2n, f2n);
+    const uint32_t w1p = pack_act2(f1p, f1p), w2p = pack_act2(f2p, f2p);
+    const uint32_t w1n = pack_act2(f1n, f1n), w2n = pack_act2(f2n, f2n);
     uint32_t* dw = reinterpret_cast<uint32_t*>(d);
-    dw[0] = w1p; dw[1] = pack_bf16x2(f1p, f2p); dw[2] = w2p;
-    dw[3] = w1n; dw[4] = pack_bf16x2(f1n, f2n); dw[5] = w2n;
+    dw[0] = w1p; dw[1] = pack_act2(f1p, f2p); dw[2] = w2p;
+    dw[3] = w1n; dw[4] = pack_act2(f1n, f2n); dw[5] = w2n;
     if (!p.x_o && p.init) {                      // device-resident recurrence, reset: o = 0
 #pragma unroll
         for (int c = 6; c < 32; ++c) dw[c] = 0u;
@@ -123,7 +140,7 @@ __global__ void pack_inputs(PackInputsParams p) {
                 }
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_act2(o[2 * c], o[2 * c + 1]);
 #pragma unroll
         for (int c = 22; c < 32; ++c) dw[c] = 0u;
     }
@@ -182,7 +199,7 @@ __global__ void emit_output(EmitParams p) {
     if (p.mi_next) {
         uint32_t* dw = reinterpret_cast<uint32_t*>(p.mi_next + row * 64);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_bf16x2(o[2 * c], o[2 * c + 1]);
+        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_act2(o[2 * c], o[2 * c + 1]);
     }
 }
 
@@ -191,36 +208,43 @@ __global__ void emit_output(EmitParams p) {
 // [w_row_base, w_row_base + n_out_pad); kmap[k] = flat offset inside one output-channel row of
 // the source, or -1 for zero padding.
 __global__ void repack_weight(const float* __restrict__ src, const int* __restrict__ kmap, int src_row_len,
-                              int n_out, int n_out_pad, int K, __nv_bfloat16* __restrict__ dst, int w_rows,
+                              int n_out, int n_out_pad, int K, act_t* __restrict__ dst, int w_rows,
                               int w_row_base) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)n_out_pad * K) return;
     const int n = (int)(idx / K), k = (int)(idx - (long)n * K);
     const int off = kmap[k];
     const float v = (n < n_out && off >= 0) ? src[(long)n * src_row_len + off] : 0.f;
-    dst[((long)(k >> 6) * w_rows + w_row_base + n) * 64 + (k & 63)] = __float2bfloat16(v);
+    dst[((long)(k >> 6) * w_rows + w_row_base + n) * 64 + (k & 63)] = to_act(v);
 }
 
 }  // namespace
 
-int launch_layernorm(const __nv_bfloat16* in, const float* gamma, const float* beta, float eps, long rows,
-                     __nv_bfloat16* out, cudaStream_t st) {
+int launch_layernorm(const act_t* in, const float* gamma, const float* beta, float eps, long rows,
+                     act_t* out, cudaStream_t st) {
     if (rows <= 0) return BMC_OK;
     layernorm_rows<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>(in, gamma, beta, eps, rows, out);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
 
-int launch_pack_nchw(const float* src, Geom g, int C, __nv_bfloat16* dst, int c_pad, int c_off, cudaStream_t st) {
+int launch_pack_nchw(const float* src, Geom g, int C, act_t* dst, int c_pad, int c_off, cudaStream_t st) {
     const long total = (long)g.B * g.H * g.W * ((C + 7) / 8);
     pack_nchw<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, g, C, dst, c_pad, c_off);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
 
-int launch_unpack_nchw(const __nv_bfloat16* src, Geom g, int C, int c_pad, int c_off, float* dst, cudaStream_t st) {
+int launch_unpack_nchw(const act_t* src, Geom g, int C, int c_pad, int c_off, float* dst, cudaStream_t st) {
     const long total = (long)g.B * g.H * g.W * ((C + 7) / 8);
     unpack_nchw<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, g, C, c_pad, c_off, dst);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_unpack_nchw_f32(const float* src, Geom g, int C, int c_pad, float* dst, cudaStream_t st) {
+    const long total = (long)g.B * g.H * g.W * ((C + 7) / 8);
+    unpack_nchw_f32<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, g, C, c_pad, dst);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
@@ -240,7 +264,7 @@ int launch_emit(const EmitParams& p, cudaStream_t st) {
 }
 
 int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out, int n_out_pad, int K,
-                            __nv_bfloat16* dst, int w_rows, int w_row_base, cudaStream_t st) {
+                            act_t* dst, int w_rows, int w_row_base, cudaStream_t st) {
     const long total = (long)n_out_pad * K;
     repack_weight<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kmap, src_row_len, n_out, n_out_pad, K, dst,
                                                                   w_rows, w_row_base);

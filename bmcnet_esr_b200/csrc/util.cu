@@ -51,7 +51,13 @@ static encode_tiled_fn get_encode() {
     return fn;
 }
 
-int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
+#ifdef BMC_ACT_BF16
+static const CUtensorMapDataType kTmapType = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+#else
+static const CUtensorMapDataType kTmapType = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+#endif
+
+int make_tmap_2d_act(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint32_t box_rows, uint32_t box_cols) {
     encode_tiled_fn enc = get_encode();
     if (!enc) {
@@ -59,7 +65,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
         return BMC_ERR_CUDA;
     }
     if (((uintptr_t)base & 15) || (cols * 2) % 16 || box_cols * 2 != 128 || box_rows > 256) {
-        set_error("make_tmap_2d_bf16: bad alignment/box (base %p cols %llu box %ux%u)", base,
+        set_error("make_tmap_2d_act: bad alignment/box (base %p cols %llu box %ux%u)", base,
                   (unsigned long long)cols, box_rows, box_cols);
         return BMC_ERR_ARG;
     }
@@ -67,7 +73,7 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
     cuuint64_t strides[1] = {cols * 2};
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+    CUresult r = enc(out, kTmapType, 2, const_cast<void*>(base), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -83,3 +89,4 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* base, uint64_t rows, uint64_
 
 extern "C" BMC_EXPORT int bmc_abi_version(void) { return BMC_ABI_VERSION; }
 extern "C" BMC_EXPORT const char* bmc_last_error(void) { return bmc::g_err; }
+extern "C" BMC_EXPORT const char* bmc_act_dtype(void) { return BMC_ACT_NAME; }

@@ -2,7 +2,7 @@
 bmc_pack_nchw, ...).  Used by the sub-module forwards in models/submodules.py and by the unit
 parity tests; the full models go through bmc_model_forward instead.
 
-Layout reminder (DESIGN.md): activations are bf16 [B*R, C] with R = roundup((H+2)*(W+2), 128);
+Layout reminder (DESIGN.md): activations are act16 [B*R, C] with R = roundup((H+2)*(W+2), 128);
 row r of image b is padded pixel (r // (W+2), r % (W+2)); halo and tail rows are zero.
 """
 import ctypes as C
@@ -25,25 +25,25 @@ def _need_cuda(*ts):
 
 
 def pack_nchw(x, c_pad=None):
-    """fp32 [B,C,H,W] -> padded NHWC bf16 [B*R, c_pad] (zero halo)."""
+    """fp32 [B,C,H,W] -> padded NHWC act16 [B*R, c_pad] (zero halo)."""
     _need_cuda(x)
     b, c, h, w = x.shape
     c_pad = c_pad or (c + 63) // 64 * 64
-    out = torch.zeros(b * rows_per_image(h, w), c_pad, dtype=torch.bfloat16, device=x.device)
+    out = torch.zeros(b * rows_per_image(h, w), c_pad, dtype=_lib.act_dtype(), device=x.device)
     x = x.contiguous().float()
     check(lib().bmc_pack_nchw(x.data_ptr(), b, c, h, w, out.data_ptr(), c_pad, 0, stream_ptr()))
     return out
 
 
 def unpack_nchw(a, b, c, h, w):
-    """padded NHWC bf16 [B*R, c_pad] -> fp32 [B,C,H,W]."""
+    """padded NHWC act16 [B*R, c_pad] -> fp32 [B,C,H,W]."""
     out = torch.empty(b, c, h, w, dtype=torch.float32, device=a.device)
     check(lib().bmc_unpack_nchw(a.data_ptr(), b, c, h, w, a.shape[1], 0, out.data_ptr(), stream_ptr()))
     return out
 
 
 def pack_conv_weight(weight, seg_channels):
-    """Conv2d weight [N, Cin, k, k] -> bf16 chunk-major [K/64, N, 64], K order (segment, tap, channel).
+    """Conv2d weight [N, Cin, k, k] -> act16 chunk-major [K/64, N, 64], K order (segment, tap, channel).
 
     `seg_channels`: list of (first input channel, count) per concatenated source; each segment is
     zero-padded to a multiple of 64 channels."""
@@ -57,15 +57,15 @@ def pack_conv_weight(weight, seg_channels):
         cols.append(seg.reshape(n, taps * pad))
     wk = torch.cat(cols, 1)                                                            # [N, K]
     k = wk.shape[1]
-    return wk.reshape(n, k // 64, 64).permute(1, 0, 2).contiguous().to(torch.bfloat16)
+    return wk.reshape(n, k // 64, 64).permute(1, 0, 2).contiguous().to(_lib.act_dtype())
 
 
 def conv_gemm(srcs, wpk, bias, b, h, w, taps, n=128, relu=False, residual=None, ln=None, impl=0,
               out_f32=False):
-    """One conv-gemm job (see include/bmc_b200.h: bmc_conv_gemm).  srcs: packed bf16 sources."""
+    """One conv-gemm job (see include/bmc_b200.h: bmc_conv_gemm).  srcs: packed act16 sources."""
     rows = b * rows_per_image(h, w)
     dev = srcs[0].device
-    out = torch.empty(rows, n, dtype=torch.bfloat16, device=dev)
+    out = torch.empty(rows, n, dtype=_lib.act_dtype(), device=dev)
     outf = torch.empty(rows, n, dtype=torch.float32, device=dev) if out_f32 else None
     j = GemmJob()
     j.n_seg = len(srcs)
@@ -76,7 +76,7 @@ def conv_gemm(srcs, wpk, bias, b, h, w, taps, n=128, relu=False, residual=None, 
     bias = None if bias is None else bias.contiguous().float()
     j.bias = bias.data_ptr() if bias is not None else None
     j.residual = residual.data_ptr() if residual is not None else None
-    j.out_bf16 = out.data_ptr(); j.out_f32 = outf.data_ptr() if out_f32 else None
+    j.out_act16 = out.data_ptr(); j.out_f32 = outf.data_ptr() if out_f32 else None
     j.relu = int(relu)
     keep = []
     if ln is not None:
@@ -89,10 +89,10 @@ def conv_gemm(srcs, wpk, bias, b, h, w, taps, n=128, relu=False, residual=None, 
 
 
 def attention_weights(centres, v, b, h, w, scale, n_split=4, impl=0):
-    """softmax(centres^T v * scale) per image -> bf16 [B, 2, 128, 64] chunk-major dynamic weights."""
+    """softmax(centres^T v * scale) per image -> act16 [B, 2, 128, 64] chunk-major dynamic weights."""
     dev = centres.device
     partial = torch.empty(b, n_split, 128, 128, dtype=torch.float32, device=dev)
-    probs = torch.empty(b * 256, 64, dtype=torch.bfloat16, device=dev)
+    probs = torch.empty(b * 256, 64, dtype=_lib.act_dtype(), device=dev)
     check(lib().bmc_attention_weights(centres.data_ptr(), v.data_ptr(), b, h, w, scale, partial.data_ptr(),
                                       n_split, probs.data_ptr(), impl, stream_ptr()))
     return probs, partial
@@ -101,13 +101,13 @@ def attention_weights(centres, v, b, h, w, scale, n_split=4, impl=0):
 def apply_dynamic_weights(v, probs, b, h, w, residual=None, impl=0):
     """out[b] = v[b] . P[b]^T (+ residual): the `softmax(att) @ v` product of BIE."""
     rows = b * rows_per_image(h, w)
-    out = torch.empty(rows, 128, dtype=torch.bfloat16, device=v.device)
+    out = torch.empty(rows, 128, dtype=_lib.act_dtype(), device=v.device)
     j = GemmJob()
     j.n_seg = 1
     j.a[0] = v.data_ptr(); j.a_rows[0] = v.shape[0]; j.a_ch[0] = 128; j.a_row_base[0] = 0
     j.w = probs.data_ptr(); j.w_rows = 128; j.w_k = 128; j.w_row_base = 0; j.w_img_stride = 256
     j.residual = residual.data_ptr() if residual is not None else None
-    j.out_bf16 = out.data_ptr()
+    j.out_act16 = out.data_ptr()
     check(lib().bmc_conv_gemm(C.byref(j), 1, 128, 1, b, h, w, impl, stream_ptr()))
     return out
 

@@ -54,10 +54,12 @@ class Engine:
 
     # -- weights --------------------------------------------------------------------------
     def _sync_weights(self, module):
-        sd = module.state_dict()
-        sig = tuple((k, v.data_ptr(), v._version, str(v.device)) for k, v in sd.items())
+        # cheap per-call change detection over the unique Parameters (54 / 24 of them):
+        # data_ptr catches .to(device) / load into new storage, _version catches in-place updates
+        sig = tuple((p.data_ptr(), p._version) for p in module.parameters())
         if sig == self.param_sig:
             return
+        sd = module.state_dict()
         dev = next(iter(sd.values())).device
         if dev.type != 'cuda':
             raise _lib.BmcError('model parameters are on %s: move the module to a CUDA device '

@@ -40,6 +40,9 @@ typedef enum {
 
 int bmc_abi_version(void);
 const char* bmc_last_error(void);
+/* "f16" (default build) or "bf16" (-DBMC_ACT_BF16): the 16-bit type of every activation / weight
+ * tensor this header calls "act16".  Accumulation is always fp32. */
+const char* bmc_act_dtype(void);
 
 /* ------------------------------------------------------------------------------------------
  * Event encoders (reference: dataloader/encodings.py).
@@ -108,7 +111,7 @@ typedef struct bmc_model bmc_model_t;
 bmc_model_t* bmc_model_create(int kind, int scale, int n_c, int n_b, int repeat);
 void bmc_model_destroy(bmc_model_t* m);
 
-/* Bytes of device memory the caller must provide for the repacked (bf16, K-major) weights. */
+/* Bytes of device memory the caller must provide for the repacked (act16, K-major) weights. */
 size_t bmc_model_weight_bytes(const bmc_model_t* m);
 
 /* Load a reference-format state_dict (318 keys for BMCNet / 120 for plain; aliases allowed and
@@ -157,7 +160,7 @@ int bmc_model_set_debug_simt(bmc_model_t* m, int enable);
 
 /* ------------------------------------------------------------------------------------------
  * Per-kernel entry points for unit parity (SURVEY section 8b "bmc_conv3x3, bmc_bie").
- * Activations are bf16 in the padded NHWC layout described in DESIGN.md:
+ * Activations are act16 in the padded NHWC layout described in DESIGN.md:
  *   rows = B * R, R = roundup((H+2)*(W+2), 128), row r of image b <-> padded pixel
  *   (r / (W+2), r % (W+2)); halo and tail rows hold zeros.
  * ---------------------------------------------------------------------------------------- */
@@ -165,19 +168,19 @@ int bmc_model_set_debug_simt(bmc_model_t* m, int enable);
 typedef struct {
     /* A operand: up to 3 concatenated sources (torch.cat along channels, e.g. BMCNet.py:64) */
     int n_seg;
-    const void* a[3];       /* device bf16 [a_rows][a_ch] */
+    const void* a[3];       /* device act16 [a_rows][a_ch] */
     int a_rows[3];
     int a_ch[3];            /* multiple of 64 */
     int a_row_base[3];      /* row of the source that pairs with output row 0 */
-    /* B operand: weights, device bf16 chunk-major [w_k/64][w_rows][64] */
+    /* B operand: weights, device act16 chunk-major [w_k/64][w_rows][64] */
     const void* w;
     int w_rows, w_k;
     int w_row_base;         /* first of the N rows used */
     int w_img_stride;       /* added per image (dynamic per-image weights, submodules.py:72-73) */
     const float* bias;      /* device float[N] or NULL */
-    const void* residual;   /* device bf16 [.][N] added after activation, or NULL */
+    const void* residual;   /* device act16 [.][N] added after activation, or NULL */
     int res_row_base;
-    void* out_bf16;         /* device bf16 [.][N] or NULL */
+    void* out_act16;         /* device act16 [.][N] or NULL */
     int out_row_base;
     float* out_f32;         /* device float [.][N] or NULL (same row base) */
     int relu;
@@ -187,7 +190,7 @@ typedef struct {
     float ln_eps;
 } bmc_gemm_job_t;
 
-/* Weights are chunk-major: w is bf16 [w_k/64][w_rows][64] (K index = (segment, tap, channel)).
+/* Weights are chunk-major: w is act16 [w_k/64][w_rows][64] (K index = (segment, tap, channel)).
  * out[m, :] = act(LN?(sum_seg sum_tap A_seg[m + dy*(W+2) + dx, :] . W[:, seg, tap, :]^T + bias)) + res
  * for all rows m of B images; n = 128 or 32 output channels; taps = 1 (1x1) or 9 (3x3, pad 1).
  * All jobs of one call share the shape and run in one launch.  impl: 0 tcgen05, 1 SIMT debug. */
@@ -195,19 +198,19 @@ int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, int n, int taps, int B
                   int impl, void* stream);
 
 /* att[b] = centres[b]^T . v[b] * scale over the pixels of image b (submodules.py:69-70), then
- * row softmax (submodules.py:72-73) written as bf16 [B][128][128] "dynamic weights".
- * centres, v: device bf16 [B*R][128]; partial: device float[B][n_split][128][128] scratch. */
+ * row softmax (submodules.py:72-73) written as act16 [B][128][128] "dynamic weights".
+ * centres, v: device act16 [B*R][128]; partial: device float[B][n_split][128][128] scratch. */
 int bmc_attention_weights(const void* centres, const void* v, int B, int H, int W, float scale,
-                          float* partial, int n_split, void* probs_bf16, int impl, void* stream);
+                          float* partial, int n_split, void* probs_act16, int impl, void* stream);
 
-/* Channel LayerNorm (submodules.py:127-139), bf16 [rows][128] -> bf16 [rows][128]. */
-int bmc_layernorm_rows(const void* in_bf16, const float* gamma, const float* beta, float eps,
-                       int64_t rows, void* out_bf16, void* stream);
+/* Channel LayerNorm (submodules.py:127-139), act16 [rows][128] -> act16 [rows][128]. */
+int bmc_layernorm_rows(const void* in_act16, const float* gamma, const float* beta, float eps,
+                       int64_t rows, void* out_act16, void* stream);
 
-/* fp32 NCHW [B,C,H,W] <-> padded NHWC bf16 [B*R][c_pad] (channels [c_off, c_off+C)). */
-int bmc_pack_nchw(const float* src, int B, int C, int H, int W, void* dst_bf16, int c_pad,
+/* fp32 NCHW [B,C,H,W] <-> padded NHWC act16 [B*R][c_pad] (channels [c_off, c_off+C)). */
+int bmc_pack_nchw(const float* src, int B, int C, int H, int W, void* dst_act16, int c_pad,
                   int c_off, void* stream);
-int bmc_unpack_nchw(const void* src_bf16, int B, int C, int H, int W, int c_pad, int c_off,
+int bmc_unpack_nchw(const void* src_act16, int B, int C, int H, int W, int c_pad, int c_off,
                     float* dst, void* stream);
 
 #ifdef __cplusplus

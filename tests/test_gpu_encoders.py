@@ -1,0 +1,175 @@
+"""GPU parity of the event encoders (csrc/encode.cu through the drop-in functions of
+bmcnet_esr_b200/dataloader/encodings.py) against the CPU oracle and the reference goldens.
+
+Bars: count-valued encodings bit-exact, incl. the reference's in-place side
+effects and quirks; float-weighted voxels within 1e-6 relative (relative to the
+largest voxel: the reference sums serially in fp32, the GPU in another order)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import encodings_np as E
+from oracle.make_golden import synth_events
+
+pytestmark = pytest.mark.gpu
+VOXEL_RTOL = 1e-6      # north_star bar for float-weighted encodings, relative to max|ref|
+
+
+@pytest.fixture(scope='module')
+def G():
+    from bmcnet_esr_b200.dataloader import encodings
+    return encodings
+
+
+def _gpu(ev):
+    return [torch.from_numpy(a.copy()).cuda() for a in ev]
+
+
+EXACT = {
+    'channels': lambda M, a, h, w, B: M.events_to_channels(a[0], a[1], a[3], sensor_size=(h, w)),
+    'stack_polarity': lambda M, a, h, w, B: M.events_to_stack_polarity(a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'stack_no_polarity': lambda M, a, h, w, B: M.events_to_stack_no_polarity(a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'voxel_torch_hard': lambda M, a, h, w, B: M.events_to_voxel_torch(a[0], a[1], a[2], a[3], B, sensor_size=(h, w),
+                                                                      temporal_bilinear=False),
+    'image': lambda M, a, h, w, B: M.events_to_image(a[0], a[1], a[3], sensor_size=(h, w)),
+    'image_torch': lambda M, a, h, w, B: M.events_to_image_torch(a[0], a[1], a[3], sensor_size=(h, w)),
+}
+FLOAT = {
+    'voxel': lambda M, a, h, w, B: M.events_to_voxel(a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'voxel_torch': lambda M, a, h, w, B: M.events_to_voxel_torch(a[0], a[1], a[2], a[3], B, sensor_size=(h, w)),
+    'image_torch_bilinear': lambda M, a, h, w, B: M.events_to_image_torch(a[0], a[1], a[3], sensor_size=(h, w),
+                                                                          interpolation='bilinear'),
+}
+
+
+def _float_close(got, ref, ev, h, w):
+    """1e-6 relative (to the largest value) while no output pixel sums more than 16 events --
+    the regime of the reference's own windows.  The reference adds serially in fp32, the GPU in
+    another order: with K events on one pixel both carry up to K half-ulps of rounding, so the
+    bar widens to 2^-24 * K for heavier pixels (e.g. the (0,0) pixel that collects every
+    out-of-range event)."""
+    xs, ys = ev[0], ev[1]
+    oor = (xs >= w) | (xs < 0) | (ys >= h) | (ys < 0)
+    pix = np.where(oor, 0, np.trunc(ys).astype(np.int64) * w + np.trunc(xs).astype(np.int64))
+    kmax = int(np.bincount(pix, minlength=1).max()) if len(pix) else 0
+    tol = max(VOXEL_RTOL, 2.0 ** -24 * kmax) * max(1.0, float(np.abs(ref).max()))
+    err = float(np.abs(got - ref).max())
+    return err <= tol, err, tol
+
+
+@pytest.mark.parametrize('fname', sorted(EXACT) + sorted(FLOAT))
+def test_against_reference_goldens(G, golden_dir, fname):
+    for path in sorted(glob.glob(os.path.join(golden_dir, 'enc_*.npz'))):
+        g = np.load(path)
+        h, w, B = int(g['h']), int(g['w']), int(g['B'])
+        a = _gpu([g['in_' + k] for k in ('xs', 'ys', 'ts', 'ps')])
+        got = (EXACT.get(fname) or FLOAT[fname])(G, a, h, w, B).cpu().numpy()
+        ref = g['out_' + fname]
+        assert got.shape == ref.shape, (path, fname)
+        if fname in EXACT:
+            assert np.array_equal(got, ref), (path, fname, float(np.abs(got - ref).max()))
+        else:
+            ok, err, tol = _float_close(got, ref, [g['in_' + k] for k in ('xs', 'ys', 'ts', 'ps')], h, w)
+            assert ok, (path, fname, err, tol)
+        for i, k in enumerate(('xs', 'ys', 'ts', 'ps')):          # in-place side effects
+            key = 'mut_%s_%s' % (fname, k)
+            want = g[key] if key in g.files else g['in_' + k]
+            assert np.array_equal(a[i].cpu().numpy(), want), (path, fname, k)
+
+
+@pytest.mark.parametrize('n,h,w,B', [(1, 5, 7, 3), (5, 5, 7, 2), (4097, 45, 80, 5), (200000, 45, 80, 5),
+                                     (150000, 180, 320, 3), (100000, 360, 640, 2), (70000, 31, 56, 9)])
+def test_against_oracle_random(G, n, h, w, B):
+    """Seeded random streams incl. out-of-range, fractional and duplicate-timestamp events; every
+    histogram tier (smem int32 / packed 16-bit / global) is hit by one of the grid sizes."""
+    ev = synth_events(n, h, w, seed=n % 97, oor=0.04, dup=True, frac=True)
+    for name, fn in {**EXACT, **FLOAT}.items():
+        ca, ga = [x.copy() for x in ev], _gpu(ev)
+        ref = fn(E, ca, h, w, B)
+        got = fn(G, ga, h, w, B).cpu().numpy()
+        assert got.shape == ref.shape, name
+        if name in EXACT:
+            assert np.array_equal(got, ref), (name, float(np.abs(got - ref).max()))
+        else:
+            ok, err, tol = _float_close(got, ref, ev, h, w)
+            assert ok, (name, err, tol)
+        for c, gt in zip(ca, ga):
+            assert np.array_equal(c, gt.cpu().numpy()), name
+
+
+def test_empty_and_unaligned_inputs(G):
+    z = torch.zeros(0, device='cuda')
+    out = G.events_to_channels(z, z.clone(), z.clone(), sensor_size=(6, 9))
+    assert out.shape == (2, 6, 9) and float(out.abs().sum()) == 0
+    # a sliced (4-byte aligned only) view must take the scalar path and still be exact
+    ev = synth_events(10001, 12, 16, seed=3, oor=0.05, frac=True)
+    full = _gpu(ev)
+    view = [t[1:].contiguous() for t in full]
+    shifted = [torch.cat([t[:1], t[1:]])[1:] for t in full]        # storage offset 1 -> unaligned
+    assert shifted[0].data_ptr() % 16 != 0
+    a = G.events_to_channels(view[0], view[1], view[3], sensor_size=(12, 16))
+    b = G.events_to_channels(shifted[0], shifted[1], shifted[3], sensor_size=(12, 16))
+    assert torch.equal(a, b)
+
+
+def test_windows_match_per_window_calls(G):
+    h, w, win = 45, 80, 2048
+    ev = synth_events(win * 37 + 111, h, w, seed=5, oor=0.02, frac=True)
+    a = _gpu(ev)
+    n = len(ev[0])
+    offs = torch.tensor(list(range(0, n, win)) + [n], dtype=torch.int64, device='cuda')
+    got = G.events_to_channels_windows(a[0], a[1], a[3], offs, sensor_size=(h, w))
+    b = _gpu(ev)
+    for i in range(len(offs) - 1):
+        s, e = int(offs[i]), int(offs[i + 1])
+        ref = E.events_to_channels(ev[0][s:e].copy(), ev[1][s:e].copy(), ev[3][s:e].copy(), sensor_size=(h, w))
+        assert np.array_equal(got[i].cpu().numpy(), ref), i
+    del b
+
+
+def test_full_size_properties(G):
+    """BASELINE sizes (1e8 events; 1e9 needs 12 GB and is exercised by bench.py): properties that do
+    not need the CPU oracle -- total count, additivity over a split of the stream, order invariance."""
+    n, h, w = 100_000_000, 45, 80
+    g = torch.Generator(device='cuda').manual_seed(1)
+    xs = torch.rand(n, device='cuda', generator=g) * w
+    ys = torch.rand(n, device='cuda', generator=g) * h
+    ps = (torch.rand(n, device='cuda', generator=g) < 0.5).float() * 2 - 1
+    full = G.events_to_channels(xs, ys, ps, sensor_size=(h, w))
+    assert float(full.sum(dtype=torch.float64)) == n
+    assert float(full[0].sum(dtype=torch.float64)) == float((ps > 0).sum())
+    k = 33_333_337
+    parts = G.events_to_channels(xs[:k].contiguous(), ys[:k].contiguous(), ps[:k].contiguous(), sensor_size=(h, w)) + \
+        G.events_to_channels(xs[k:].contiguous(), ys[k:].contiguous(), ps[k:].contiguous(), sensor_size=(h, w))
+    assert torch.equal(full, parts)
+    perm = torch.randperm(n, device='cuda', generator=g)
+    assert torch.equal(full, G.events_to_channels(xs[perm], ys[perm], ps[perm], sensor_size=(h, w)))
+    # oracle on a 2e6 prefix, and the HR grid through the 16-bit packed tier with a hot pixel
+    m = 2_000_000
+    ref = E.events_to_channels(xs[:m].cpu().numpy(), ys[:m].cpu().numpy(), ps[:m].cpu().numpy(), sensor_size=(h, w))
+    assert np.array_equal(G.events_to_channels(xs[:m].contiguous(), ys[:m].contiguous(), ps[:m].contiguous(),
+                                               sensor_size=(h, w)).cpu().numpy(), ref)
+    xh = xs[:20_000_000] * 4
+    yh = ys[:20_000_000] * 4
+    xh[:5_000_000] = 17.0          # 5e6 events on one pixel: forces the 16-bit carry path many times
+    yh[:5_000_000] = 3.0
+    ph = torch.ones_like(xh)
+    hr = G.events_to_channels(xh, yh, ph, sensor_size=(180, 320))
+    assert float(hr.sum(dtype=torch.float64)) == 20_000_000
+    assert float(hr[0, 180 - 1 - 3, 17]) >= 5_000_000
+    cnt = torch.zeros(180 * 320, device='cuda', dtype=torch.float64)
+    cnt.index_add_(0, ((180 - 1 - yh.long()) * 320 + xh.long()), torch.ones_like(xh, dtype=torch.float64))
+    assert torch.equal(hr[0].double().flatten(), cnt)
+
+
+def test_fp32_saturation_matches_reference_semantics(G):
+    # the reference adds 1.0f serially and sticks at 2^24; 2^24 + 1000 events on one pixel
+    n = (1 << 24) + 1000
+    xs = torch.full((n,), 2.0, device='cuda')
+    ys = torch.full((n,), 1.0, device='cuda')
+    ps = torch.ones(n, device='cuda')
+    out = G.events_to_channels(xs, ys, ps, sensor_size=(4, 4))
+    assert float(out[0, 4 - 1 - 1, 2]) == float(1 << 24)
