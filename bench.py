@@ -145,7 +145,9 @@ def main():
     ap.add_argument('--steps', type=int, default=100)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--workload', default='plain_nfs', choices=sorted(WORKLOADS))
-    ap.add_argument('--batch', type=int, default=16, help='independent sequences per GPU, stepped in lockstep')
+    ap.add_argument('--batch', type=int, default=0,
+                    help='independent sequences per GPU, stepped in lockstep (default: per workload, chosen so the '
+                         '256-row conv tiles fill whole waves of the 148 SMs)')
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--cpu-steps', type=int, default=12)
     args = ap.parse_args()
@@ -155,6 +157,9 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     model_kind, h, w, n_win, desc = WORKLOADS[args.workload]
+    if args.batch <= 0:
+        # tiles per conv job = ceil(B * R / 256), R = roundup((H+2)(W+2), 128): 19 x 3968 / 256 = 295 ~ 2 x 148
+        args.batch = {'plain_nfs': 19, 'bmcnet_nfs': 19, 'bmcnet_eventzoom': 39}[args.workload]
     config = {'workload': desc, 'batch_per_gpu': args.batch, 'lr_hw': [h, w], 'events_per_window': n_win,
               'windows_per_step_per_sequence': 2, 'sharding': 'independent sequences per GPU, no collective'}
 

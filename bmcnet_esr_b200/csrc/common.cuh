@@ -214,6 +214,20 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
     d |= (uint64_t)2 << 61;
     return d;
 }
+// The MMA-issuing thread is alone in its warp, so every scalar instruction between two
+// tcgen05.mma costs its full latency.  Descriptors are therefore split: the high word is a
+// compile-time constant per layout, the low word (start address >> 4 | LBO field) advances by a
+// plain 32-bit add.
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
+}
+__device__ __forceinline__ uint64_t umma_desc(uint32_t lo, uint32_t hi) {
+    return ((uint64_t)hi << 32) | lo;
+}
+
 // Instruction descriptor (cute::UMMA::InstrDescriptor): act_t x act_t -> fp32, M x N tile.
 #ifdef BMC_ACT_BF16
 #define BMC_UMMA_FMT 1u                    // F16F32Format::BF16
@@ -247,8 +261,9 @@ __device__ __forceinline__ float from_act(act_t a) { return __bfloat162float(a);
 // fp16 saturates at +-65504 instead of overflowing to inf
 __device__ __forceinline__ float sat_h(float f) { return fminf(fmaxf(f, -65504.f), 65504.f); }
 __device__ __forceinline__ uint32_t pack_act2(float lo, float hi) {
-    __half2 v = __floats2half2_rn(sat_h(lo), sat_h(hi));
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;       // one F2FP.SATFINITE: round to nearest, clamp to +-65504 (first operand -> upper half)
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
 }
 __device__ __forceinline__ float2 unpack_act2(uint32_t u) {
     __half2 v = *reinterpret_cast<__half2*>(&u);

@@ -23,7 +23,8 @@ constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
 
 struct GemmJobDev {
-    int a_map[kMaxSeg];        // index into GemmParams::maps
+    int a_map[kMaxSeg];        // index into GemmParams::maps: box [128 rows x 64 ch]
+    int a_map64[kMaxSeg];      // same tensor, box [64 rows x 64 ch] (slab kernel), or -1
     int a_row_base[kMaxSeg];   // row of the source paired with output row 0
     int a_col_base[kMaxSeg];   // first channel used
     const act_t* a_ptr[kMaxSeg];   // same sources as raw pointers (SIMT kernel)
@@ -59,6 +60,9 @@ struct alignas(64) GemmParams {
     int n;                     // output channels: 128 or 32
     Geom g;
     int tiles_per_img;         // R / 128
+    // slab kernel (gemm_slab.cu); filled in by its launcher
+    int slab_lead, slab_boxes, tiles_per_job, bo_mode;
+    long long* prof;           // optional per-CTA cycle counters (tools/gpu_diag.py slabprof), else NULL
 };
 
 static_assert(sizeof(GemmParams) <= 4096, "GemmParams must fit the classic 4 KB kernel parameter space");
@@ -84,7 +88,10 @@ struct SoftmaxParams {
     int w_img_stride;                      // w_row_base[pair] + b * w_img_stride
 };
 
-// Launchers (host).  `impl`: 0 = tcgen05/TMA, 1 = SIMT cross-check.
+// Launchers (host).  `impl`: 0 = tcgen05/TMA (slab kernel when it applies, else the per-tap
+// kernel), 1 = SIMT cross-check, 2 = force the per-tap tcgen05 kernel.
+bool slab_supported(const GemmParams& p);
+int launch_conv_slab(GemmParams p, cudaStream_t st);
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st);
 int launch_att(const AttParams& p, int impl, cudaStream_t st);
 int launch_att_softmax(const SoftmaxParams& p, cudaStream_t st);

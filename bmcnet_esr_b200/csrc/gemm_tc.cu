@@ -9,7 +9,7 @@
 //               halo masking, bf16 (and optional fp32) stores
 //   smem ring of kStages {A 16 KB, B N*128 B} tiles in the 128-byte-swizzled K-major layout, full /
 //   empty mbarriers; tcgen05.commit releases a stage when the MMAs that read it are done.
-#include "gemm.cuh"
+#include "gemm_epi.cuh"
 
 namespace bmc {
 namespace {
@@ -25,14 +25,14 @@ struct TcCfg {
 };
 
 template <int N, int STAGES>
-__global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant__ GemmParams p) {
+__global__ void __launch_bounds__(kThreadsTc, 2) conv_gemm_tc(const __grid_constant__ GemmParams p) {
     using Cfg = TcCfg<N>;
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     // dynamic smem base is only guaranteed 16-byte aligned: realign to 1024 for SWIZZLE_128B
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], acc_bar;
     __shared__ uint32_t tmem_base_s;
-    __shared__ float bias_s[N], gamma_s[N], beta_s[N];
+    __shared__ __align__(16) float bias_s[N], gamma_s[N], beta_s[N];
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -93,14 +93,14 @@ __global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant
                 mbar_wait(&full_bar[st], (it / STAGES) & 1);
                 tc_fence_after_sync();
                 const uint32_t sa = smem_u32(smem + st * Cfg::kStageBytes);
-                const uint32_t sb = sa + Cfg::kABytes;
+                // K-major SWIZZLE_128B: 8-row groups 1024 B apart; +32 B (2 x 16 B) per K=16 slice
+                const uint32_t a_lo = umma_desc_lo(sa, 16), b_lo = umma_desc_lo(sa + Cfg::kABytes, 16);
+                constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+                const uint32_t acc_first = it > 0 ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < kChunkK / 16; ++k) {
-                    // K-major SWIZZLE_128B: 8-row groups 1024 B apart; +32 B per K=16 slice
-                    const uint64_t da = umma_smem_desc_sw128(sa + k * 32, 16, 1024);
-                    const uint64_t db = umma_smem_desc_sw128(sb + k * 32, 16, 1024);
-                    umma_f16(tmem_acc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < kChunkK / 16; ++k)
+                    umma_f16(tmem_acc, umma_desc(a_lo + k * 2, hi), umma_desc(b_lo + k * 2, hi), idesc,
+                             k == 0 ? acc_first : 1u);
                 umma_commit(&empty_bar[st]);       // stage reusable once these MMAs retire
             }
             umma_commit(&acc_bar);                 // accumulator complete
@@ -115,81 +115,21 @@ __global__ void __launch_bounds__(kThreadsTc) conv_gemm_tc(const __grid_constant
         const bool valid = p.g.interior(r_img, y, x);
         mbar_wait(&acc_bar, 0);
         tc_fence_after_sync();
-        const act_t* res = job.residual ? job.residual + (job.res_row_base + m) * N : nullptr;
-        act_t* out = job.out ? job.out + (job.out_row_base + m) * N : nullptr;
-        float* outf = job.out_f32 ? job.out_f32 + (job.out_row_base + m) * N : nullptr;
+        EpiRow r;
+        r.res = job.residual ? job.residual + (job.res_row_base + m) * N : nullptr;
+        r.out = job.out ? job.out + (job.out_row_base + m) * N : nullptr;
+        r.outf = job.out_f32 ? job.out_f32 + (job.out_row_base + m) * N : nullptr;
+        r.valid = valid; r.store = true; r.relu = job.relu != 0; r.ln_eps = job.ln_eps;
         const uint32_t trow = tmem_acc + ((uint32_t)(q * 32) << 16);
-        // Fused channel LayerNorm: this thread owns the whole row, so mean / variance are
-        // thread-local; two extra passes over TMEM (16 TB/s) instead of an HBM round trip.
         const bool ln = job.ln_gamma != nullptr;
         float mu = 0.f, rstd = 1.f;
-        if (ln) {
-            float s1 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < N / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(trow + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) s1 += __uint_as_float(v[j]) + bias_s[c * 32 + j];
-            }
-            mu = s1 * (1.f / N);
-            float s2 = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < N / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld_32x32(trow + c * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float d = __uint_as_float(v[j]) + bias_s[c * 32 + j] - mu;
-                    s2 += d * d;
-                }
-            }
-            rstd = 1.f / sqrtf(s2 * (1.f / N) + job.ln_eps);
-        }
+        if (ln) epi_ln_stats<N>(trow, bias_s, job.ln_eps, mu, rstd);
 #pragma unroll 1
         for (int c = 0; c < N / 32; ++c) {
             uint32_t v[32];
             tmem_ld_32x32(trow + c * 32, v);
             tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                f[j] = __uint_as_float(v[j]) + bias_s[c * 32 + j];
-                if (ln) f[j] = gamma_s[c * 32 + j] * ((f[j] - mu) * rstd) + beta_s[c * 32 + j];
-                if (job.relu) f[j] = fmaxf(f[j], 0.f);
-            }
-            if (res) {
-                const uint4* rp = reinterpret_cast<const uint4*>(res + c * 32);
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const uint4 rv = valid ? rp[u] : make_uint4(0, 0, 0, 0);
-                    const uint32_t w[4] = {rv.x, rv.y, rv.z, rv.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 t = unpack_act2(w[e]);
-                        f[u * 8 + e * 2] += t.x;
-                        f[u * 8 + e * 2 + 1] += t.y;
-                    }
-                }
-            }
-            if (!valid) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = 0.f;
-            }
-            if (out) {
-                uint4* op = reinterpret_cast<uint4*>(out + c * 32);
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    op[u] = make_uint4(pack_act2(f[u * 8], f[u * 8 + 1]), pack_act2(f[u * 8 + 2], f[u * 8 + 3]),
-                                       pack_act2(f[u * 8 + 4], f[u * 8 + 5]), pack_act2(f[u * 8 + 6], f[u * 8 + 7]));
-            }
-            if (outf) {
-                float4* op = reinterpret_cast<float4*>(outf + c * 32);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) op[u] = make_float4(f[u * 4], f[u * 4 + 1], f[u * 4 + 2], f[u * 4 + 3]);
-            }
+            epi_chunk(v, c, r, bias_s, ln, mu, rstd, gamma_s, beta_s);
         }
     }
     tc_fence_before_sync();
@@ -256,15 +196,15 @@ __global__ void __launch_bounds__(kThreadsTc) att_tc(const __grid_constant__ Att
                 mbar_wait(&full_bar[st], (it / kAttStages) & 1);
                 tc_fence_after_sync();
                 const uint32_t sa = smem_u32(smem + st * kAttStageBytes);
-                const uint32_t sb = sa + 2 * kAttBox;
+                // MN-major SWIZZLE_128B: 64-channel blocks LBO = 8192 B apart, 8-pixel groups
+                // SBO = 1024 B apart; one K=16 slice = 16 pixel rows = 2048 B (128 x 16 B).
+                const uint32_t a_lo = umma_desc_lo(sa, kAttBox), b_lo = umma_desc_lo(sa + 2 * kAttBox, kAttBox);
+                constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+                const uint32_t acc_first = it > 0 ? 1u : 0u;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    // MN-major SWIZZLE_128B: 64-channel blocks LBO = 8192 B apart, 8-pixel groups
-                    // SBO = 1024 B apart; one K=16 slice = 16 pixel rows = 2048 B.
-                    const uint64_t da = umma_smem_desc_sw128(sa + k * 2048, kAttBox, 1024);
-                    const uint64_t db = umma_smem_desc_sw128(sb + k * 2048, kAttBox, 1024);
-                    umma_f16(tmem_acc, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
-                }
+                for (int k = 0; k < 4; ++k)
+                    umma_f16(tmem_acc, umma_desc(a_lo + k * 128, hi), umma_desc(b_lo + k * 128, hi), idesc,
+                             k == 0 ? acc_first : 1u);
                 umma_commit(&empty_bar[st]);
             }
             umma_commit(&acc_bar);
@@ -324,6 +264,9 @@ int launch_att_simt(const AttParams& p, cudaStream_t st);
 
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
     if (impl == 1) return launch_conv_gemm_simt(p, st);
+    static int use_slab = -1;
+    if (use_slab < 0) { const char* e = getenv("BMC_CONV_SLAB"); use_slab = e ? atoi(e) : 1; }
+    if (impl == 0 && use_slab && p.jobs[0].a_map64[0] >= 0 && slab_supported(p)) return launch_conv_slab(p, st);
     static int stages = 0;
     if (stages == 0) {
         const char* e = getenv("BMC_TC_STAGES");

@@ -160,7 +160,7 @@ struct bmc_model {
     size_t ws_bytes = 0;
     size_t off_mi = 0, off_a32 = 0, off_p = 0, off_partial = 0, off_hid32 = 0;
     char* ws = nullptr;
-    CUtensorMap map_act, map_att, map_mi, map_w128, map_w32, map_p;
+    CUtensorMap map_act, map_att, map_mi, map_mi64, map_w128, map_w32, map_p;
     // plan
     std::vector<Op> ops;
     std::vector<int> free_slots;
@@ -289,6 +289,8 @@ struct Builder {
         p.maps[0] = m->map_act; p.maps[1] = m->map_mi;
         p.maps[2] = (n == 32) ? m->map_w32 : m->map_w128;
         p.maps[3] = m->map_p;
+        p.maps[4] = m->map_att;                 // act arena, 64-row boxes (slab kernel)
+        p.maps[5] = m->map_mi64;
         p.n_jobs = (int)jobs.size();
         p.n_seg = (int)jobs[0].segs.size();
         p.n_taps = taps;
@@ -301,9 +303,9 @@ struct Builder {
             for (int s = 0; s < p.n_seg; ++s) {
                 const Src& src = js.segs[s];
                 if (src.kind == 1) {
-                    d.a_map[s] = 1; d.a_row_base[s] = 0; d.a_ptr[s] = m->mi_ptr(); d.a_ld[s] = 64; d.a_rows[s] = g.rows();
+                    d.a_map[s] = 1; d.a_map64[s] = 5; d.a_row_base[s] = 0; d.a_ptr[s] = m->mi_ptr(); d.a_ld[s] = 64; d.a_rows[s] = g.rows();
                 } else {
-                    d.a_map[s] = 0; d.a_row_base[s] = (int)(src.slot * g.rows());
+                    d.a_map[s] = 0; d.a_map64[s] = 4; d.a_row_base[s] = (int)(src.slot * g.rows());
                     d.a_ptr[s] = m->slot_ptr(0); d.a_ld[s] = 128; d.a_rows[s] = (long)m->n_slots * g.rows();
                 }
                 d.a_col_base[s] = 0;
@@ -716,6 +718,7 @@ extern "C" BMC_EXPORT int bmc_model_bind_workspace(bmc_model_t* m, void* workspa
     int rc = make_tmap_2d_act(&m->map_act, m->slot_ptr(0), rows * m->n_slots, 128, 128, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_att, m->slot_ptr(0), rows * m->n_slots, 128, 64, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_mi, m->mi_ptr(), rows, 64, 128, 64);
+    if (!rc) rc = make_tmap_2d_act(&m->map_mi64, m->mi_ptr(), rows, 64, 64, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_p, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128, 64);
     if (rc) return rc;
     m->dry = false;
@@ -811,17 +814,18 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
     for (int t = 0; t < taps; ++t) p.tap_off[t] = taps == 9 ? (t / 3 - 1) * g.Wp + (t % 3 - 1) : 0;
     for (int s = 0; s < p.n_seg; ++s) p.chunks[s] = jobs[0].a_ch[s] / 64;
     int n_maps = 0;
-    std::vector<const void*> map_key;
+    std::vector<std::pair<const void*, uint32_t>> map_key;
     auto get_map = [&](const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, int* idx) -> int {
         for (size_t i = 0; i < map_key.size(); ++i)
-            if (map_key[i] == ptr) { *idx = (int)i; return BMC_OK; }
-        BMC_REQUIRE(n_maps < kMaxMaps, "conv_gemm: more than %d distinct operand tensors in one call", kMaxMaps);
-        int rc = impl == 0 ? make_tmap_2d_act(&p.maps[n_maps], ptr, rows, cols, box_rows, 64) : BMC_OK;
+            if (map_key[i].first == ptr && map_key[i].second == box_rows) { *idx = (int)i; return BMC_OK; }
+        if (n_maps >= kMaxMaps) { *idx = -1; return BMC_OK; }
+        int rc = impl != 1 ? make_tmap_2d_act(&p.maps[n_maps], ptr, rows, cols, box_rows, 64) : BMC_OK;
         if (rc) return rc;
-        map_key.push_back(ptr);
+        map_key.push_back({ptr, box_rows});
         *idx = n_maps++;
         return BMC_OK;
     };
+    bool maps64_ok = true;
     for (int j = 0; j < n_jobs; ++j) {
         const bmc_gemm_job_t& js = jobs[j];
         GemmJobDev& d = p.jobs[j];
@@ -831,6 +835,7 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
             BMC_REQUIRE(js.a[s] && js.a_ch[s] % 64 == 0 && js.a_ch[s] / 64 == p.chunks[s], "conv_gemm: bad segment %d", s);
             int rc = get_map(js.a[s], (uint64_t)js.a_rows[s], (uint64_t)js.a_ch[s], 128, &d.a_map[s]);
             if (rc) return rc;
+            BMC_REQUIRE(d.a_map[s] >= 0, "conv_gemm: more than %d distinct operand tensors in one call", kMaxMaps);
             d.a_row_base[s] = js.a_row_base[s]; d.a_col_base[s] = 0;
             d.a_ptr[s] = static_cast<const act_t*>(js.a[s]); d.a_ld[s] = js.a_ch[s]; d.a_rows[s] = js.a_rows[s];
             kch += p.chunks[s] * taps;
@@ -839,6 +844,7 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
         const uint64_t w_total = (uint64_t)js.w_row_base + (uint64_t)(B - 1) * js.w_img_stride + (uint64_t)js.w_rows * kch;
         int rc = get_map(js.w, w_total, 64, (uint32_t)n, &d.w_map);
         if (rc) return rc;
+        BMC_REQUIRE(d.w_map >= 0, "conv_gemm: more than %d distinct operand tensors in one call", kMaxMaps);
         d.w_ptr = static_cast<const act_t*>(js.w); d.w_rows = js.w_rows;
         d.w_row_base = js.w_row_base; d.w_img_stride = js.w_img_stride;
         d.bias = js.bias; d.relu = js.relu;
@@ -846,6 +852,16 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
         d.out = static_cast<act_t*>(js.out_act16); d.out_row_base = js.out_row_base; d.out_f32 = js.out_f32;
         d.ln_gamma = js.ln_gamma; d.ln_beta = js.ln_beta; d.ln_eps = js.ln_eps;
     }
+    // 64-row-box descriptors for the slab kernel, if they still fit; otherwise the per-tap kernel runs
+    for (int j = 0; j < n_jobs && maps64_ok; ++j)
+        for (int s = 0; s < p.n_seg && maps64_ok; ++s) {
+            int rc = get_map(jobs[j].a[s], (uint64_t)jobs[j].a_rows[s], (uint64_t)jobs[j].a_ch[s], 64, &p.jobs[j].a_map64[s]);
+            if (rc) return rc;
+            if (p.jobs[j].a_map64[s] < 0) maps64_ok = false;
+        }
+    if (!maps64_ok)
+        for (int j = 0; j < n_jobs; ++j)
+            for (int s = 0; s < kMaxSeg; ++s) p.jobs[j].a_map64[s] = -1;
     return launch_conv_gemm(p, impl, as_stream(stream));
 }
 

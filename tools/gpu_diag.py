@@ -199,6 +199,49 @@ def perf_case():
             print('  conv3x3 128->128 B=%d rows=%d: %.1f us  %.1f TFLOP/s (padded rows) ' % (b, rows, ms * 1e3, 2 * rows * 1152 * 128 / ms / 1e9))
 
 
+def convperf_case():
+    import ctypes as C
+    import torch
+    from bmcnet_esr_b200 import _lib, kernels as K
+    h, w = 45, 80
+    for taps, segs in ((9, 1), (1, 1), (1, 2)):
+        for jobs in (2,):
+            for b in (1, 4, 16, 19):
+                for impl in (0, 2):
+                    src = [K.pack_nchw(torch.randn(b, 128, h, w, device='cuda')) for _ in range(jobs * segs)]
+                    wt = torch.randn(128, 128 * segs, 3 if taps == 9 else 1, 3 if taps == 9 else 1, device='cuda') * 0.03
+                    wpk = K.pack_conv_weight(wt, [(i * 128, 128) for i in range(segs)])
+                    bias = torch.zeros(128, device='cuda')
+                    outs = [torch.empty_like(src[0]) for _ in range(jobs)]
+                    jarr = (_lib.GemmJob * jobs)()
+                    for j in range(jobs):
+                        jarr[j].n_seg = segs
+                        for sg in range(segs):
+                            t = src[j * segs + sg]
+                            jarr[j].a[sg] = t.data_ptr(); jarr[j].a_rows[sg] = t.shape[0]; jarr[j].a_ch[sg] = 128
+                        jarr[j].w = wpk.data_ptr(); jarr[j].w_rows = 128; jarr[j].w_k = wpk.shape[0] * 64
+                        jarr[j].bias = bias.data_ptr(); jarr[j].out_act16 = outs[j].data_ptr(); jarr[j].relu = 1
+                    launch = lambda: _lib.check(_lib.lib().bmc_conv_gemm(jarr, jobs, 128, taps, b, h, w, impl, _lib.stream_ptr()))
+                    for _ in range(3):
+                        launch()
+                    torch.cuda.synchronize()
+                    reps = 20
+                    g = torch.cuda.CUDAGraph()
+                    side = torch.cuda.Stream()
+                    with torch.cuda.stream(side):
+                        with torch.cuda.graph(g, stream=side):
+                            for _ in range(reps):
+                                launch()
+                    g.replay()
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record(); g.replay(); e1.record()
+                    torch.cuda.synchronize()
+                    us = e0.elapsed_time(e1) / reps * 1e3
+                    fl = 2.0 * 128 * 128 * segs * taps * h * w * b * jobs
+                    print('  taps=%d segs=%d jobs=%d B=%2d impl=%d: %7.1f us  %7.1f TFLOP/s (real px)' % (taps, segs, jobs, b, impl, us, fl / us / 1e6))
+
+
 def run_stage(name):
     import torch
     print('== stage', name, flush=True)
@@ -231,6 +274,8 @@ def run_stage(name):
         model_case(False, True, h=12, w=20)
     elif name == 'full_tc':
         model_case(False, False)
+    elif name == 'convperf':
+        convperf_case()
     elif name == 'perf':
         perf_case()
     elif name == 'step_tc':
@@ -246,9 +291,17 @@ if __name__ == '__main__':
         sys.exit(0)
     stages = sys.argv[1:] or STAGES
     for s in stages:
+        env = dict(os.environ)
+        name = s
+        if '@' in s:                      # stage@VAR=val,VAR2=val2
+            name, kv = s.split('@', 1)
+            for item in kv.split(','):
+                k, v = item.split('=', 1)
+                env[k] = v
+            print('## env', kv)
         try:
-            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--stage', s], timeout=300,
-                               capture_output=True, text=True)
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), '--stage', name], timeout=300,
+                               capture_output=True, text=True, env=env)
             print(r.stdout[-6000:])
             if r.returncode != 0:
                 print('!! stage %s exit code %d\n%s' % (s, r.returncode, r.stderr[-3000:]))
