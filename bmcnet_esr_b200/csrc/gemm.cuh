@@ -62,6 +62,8 @@ struct alignas(64) GemmParams {
     int tiles_per_img;         // R / 128
     // slab kernel (gemm_slab.cu); filled in by its launcher
     int slab_lead, slab_boxes, tiles_per_job, bo_mode;
+    int per_image;             // tiles never straddle images (per-image dynamic weights); tiles_per_img256 each
+    int tiles_per_img256;
     long long* prof;           // optional per-CTA cycle counters (tools/gpu_diag.py slabprof), else NULL
 };
 

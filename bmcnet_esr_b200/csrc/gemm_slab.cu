@@ -41,11 +41,12 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int slab_bytes = p.slab_boxes * kBoxBytes;
     uint8_t* smem_w = smem + kSlabStages * slab_bytes;
+    uint8_t* smem_stage = smem_w + kWStages * kWStageBytes;      // 8 epilogue warps x 2 KB
 
     __shared__ uint64_t a_full[kSlabStages], a_empty[kSlabStages], w_full[kWStages], w_empty[kWStages];
     __shared__ uint64_t acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float bias_s[2][N], gamma_s[2][N], beta_s[2][N];
+    __shared__ __align__(16) float bias_s[2][N];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_job = p.tiles_per_job;
@@ -68,6 +69,17 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             seg_chunk0 += n_taps * p.chunks[s];
         }
     }
+    // tile -> (first row, one-past-last storable row, image for per-image weights)
+    auto tile_rows = [&](int tile, long& m0, long& m_end, int& img) {
+        const int rem = tile % tiles_per_job;
+        if (p.per_image) {
+            img = rem / p.tiles_per_img256;
+            m0 = (long)img * p.g.R + (long)(rem - img * p.tiles_per_img256) * kBM;
+            m_end = (long)(img + 1) * p.g.R;
+        } else {
+            img = 0; m0 = (long)rem * kBM; m_end = rows_total;
+        }
+    };
     const int steps = a_steps * n_taps;                 // K steps (one tap of one chunk) per tile
     const int groups = (steps + kWGroup - 1) / kWGroup; // weight stages per tile
 
@@ -90,7 +102,9 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             int it = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const GemmJobDev& job = p.jobs[tile / tiles_per_job];
-                const int m0 = (tile % tiles_per_job) * kBM;
+                long m0l, m_end; int img;
+                tile_rows(tile, m0l, m_end, img);
+                const int m0 = (int)m0l;
                 for (int as = 0; as < a_steps; ++as, ++it) {
                     const int s = as_seg[as];
                     const int st = it % kSlabStages;
@@ -114,6 +128,9 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const GemmJobDev& job = p.jobs[tile / tiles_per_job];
                 const CUtensorMap* map = &p.maps[job.w_map];
+                long m0l, m_end; int img;
+                tile_rows(tile, m0l, m_end, img);
+                const int w_row0 = job.w_row_base + img * job.w_img_stride;
                 int as = 0, tap = 0;
                 for (int g = 0; g < groups; ++g, ++gi) {
                     const int st = gi % kWStages;
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     for (int j = 0; j < cnt; ++j) {
                         const int kchunk = as_k0[as] + tap * as_cs[as];                    // K order (seg, tap, chunk)
                         tma_load_2d(smem_w + st * kWStageBytes + j * kWBytes, map, &w_full[st], 0,
-                                    kchunk * job.w_rows + job.w_row_base);
+                                    kchunk * job.w_rows + w_row0);
                         if (++tap == n_taps) { tap = 0; ++as; }
                     }
                 }
@@ -204,29 +221,30 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
             const int buf = lt & 1;
             const GemmJobDev& job = p.jobs[tile / tiles_per_job];
-            const long m = (long)(tile % tiles_per_job) * kBM + hf * 128 + q * 32 + lane;
+            long m0l, m_end; int img_t;
+            tile_rows(tile, m0l, m_end, img_t);
+            const long m = m0l + hf * 128 + q * 32 + lane;
             // per-tile channel vectors (the job can change from tile to tile)
             {
                 const int t = threadIdx.x;                // 0..255
-                if (t < N) {
-                    bias_s[buf][t] = job.bias ? job.bias[t] : 0.f;
-                    gamma_s[buf][t] = job.ln_gamma ? job.ln_gamma[t] : 1.f;
-                    beta_s[buf][t] = job.ln_gamma ? job.ln_beta[t] : 0.f;
-                }
+                if (t < N) bias_s[buf][t] = job.bias ? job.bias[t] : 0.f;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const int img = (int)(m / p.g.R);
             const int r_img = (int)(m - (long)img * p.g.R);
             int y, x;
-            const bool in_range = m < rows_total;
+            const bool in_range = m < m_end;
             const bool valid = in_range && p.g.interior(r_img, y, x);
             { PROF_T0(); mbar_wait(&acc_full[buf], (lt >> 1) & 1); PROF_ADD(w0); }
             tc_fence_after_sync();
-            EpiRow r;
-            r.res = job.residual ? job.residual + (job.res_row_base + m) * N : nullptr;
-            r.out = job.out ? job.out + (job.out_row_base + m) * N : nullptr;
+            const long m_warp = m - lane;                  // first row of this warp's 32-row block
+            EpiTile r;
+            r.res = job.residual ? job.residual + (job.res_row_base + m_warp) * N : nullptr;
+            r.out = job.out ? job.out + (job.out_row_base + m_warp) * N : nullptr;
             r.outf = job.out_f32 ? job.out_f32 + (job.out_row_base + m) * N : nullptr;
-            r.valid = valid; r.store = in_range && !(p.bo_mode & 2); r.relu = job.relu != 0; r.ln_eps = job.ln_eps;
+            r.rows_left = (p.bo_mode & 2) ? 0 : m_end - m_warp;
+            r.valid = valid; r.relu = job.relu != 0; r.n = N;
+            uint8_t* stage = smem_stage + warp * 2048;
             const uint32_t trow = tmem_base + buf * 2 * N + hf * N + ((uint32_t)(q * 32) << 16);
             const bool ln = job.ln_gamma != nullptr;
             float mu = 0.f, rstd = 1.f;
@@ -247,7 +265,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     tc_fence_before_sync();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
-                epi_chunk(v, c, r, bias_s[buf], ln, mu, rstd, gamma_s[buf], beta_s[buf]);
+                epi_chunk_staged(v, c, r, bias_s[buf], ln, mu, rstd, job.ln_gamma, job.ln_beta, stage, lane);   // gamma/beta: L1-resident broadcast loads
                 if (prof_on) w2 += clock64() - _ts;
             }
         }
@@ -267,7 +285,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
 template <int N>
 int launch_slab_n(const GemmParams& p, cudaStream_t st) {
     auto kern = conv_slab_tc<N>;
-    const int smem = kSlabStages * p.slab_boxes * kBoxBytes + kWStages * kWGroup * N * kChunkK * 2 + 1024;
+    const int smem = kSlabStages * p.slab_boxes * kBoxBytes + kWStages * kWGroup * N * kChunkK * 2 + 8 * 2048 + 1024;
     static int configured = 0;
     if (configured < smem) {
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -285,18 +303,19 @@ int launch_slab_n(const GemmParams& p, cudaStream_t st) {
 // Largest padded row pitch the slab ring fits in shared memory for (2 x slab + 4 x 16 KB weights).
 bool slab_supported(const GemmParams& p) {
     if (p.n != 128 && p.n != 32) return false;
-    for (int j = 0; j < p.n_jobs; ++j)
-        if (p.jobs[j].w_img_stride != 0) return false;          // per-image weights need per-image tiles
     const int lead = p.n_taps == 9 ? p.g.Wp + 1 : 0;
     const int boxes = (kBM + 2 * lead + kBoxRows - 1) / kBoxRows;
-    const int smem = kSlabStages * boxes * kBoxBytes + kWStages * kWGroup * p.n * kChunkK * 2 + 1024;
-    return smem + 4096 <= 227 * 1024;
+    const int smem = kSlabStages * boxes * kBoxBytes + kWStages * kWGroup * p.n * kChunkK * 2 + 8 * 2048 + 1024;
+    return smem + 2048 <= 227 * 1024;
 }
 
 int launch_conv_slab(GemmParams p, cudaStream_t st) {
     p.slab_lead = p.n_taps == 9 ? p.g.Wp + 1 : 0;
     p.slab_boxes = (kBM + 2 * p.slab_lead + kBoxRows - 1) / kBoxRows;
-    p.tiles_per_job = (int)((p.g.rows() + kBM - 1) / kBM);
+    p.per_image = 0;
+    for (int j = 0; j < p.n_jobs; ++j) p.per_image |= p.jobs[j].w_img_stride != 0;   // per-image weights: per-image tiles
+    p.tiles_per_img256 = (p.g.R + kBM - 1) / kBM;
+    p.tiles_per_job = p.per_image ? p.g.B * p.tiles_per_img256 : (int)((p.g.rows() + kBM - 1) / kBM);
     static int bo = -1;
     // 0 (default, verified on B200): the hardware swizzles on absolute shared-memory address bits,
     // so a row-shifted start needs no base offset; 1 sets the descriptor's base-offset field
