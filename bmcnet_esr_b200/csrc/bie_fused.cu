@@ -1,0 +1,724 @@
+// Fused 1x1 / attention section of BIE.forward (reference models/submodules.py:63-75).
+//
+// The unfused dataflow (model.cu, kept for the SIMT cross-check) materialises 28 activation-sized
+// tensors per BIE call: convf+LN, clustering, v1/v2, att, softmax(att)@v, unclustering.  Two
+// algebraic facts remove almost all of them:
+//   * v_k = Wv_k x_k + bv_k is only ever contracted:  att_k = c_k^T v_k = (c_k^T x_k) Wv_k^T + (sum_px c_k) bv_k^T
+//     and out_k = softmax(att_k) v_k = (P_k Wv_k) x_k + P_k bv_k.  So v is never formed: the attention
+//     logits come from G_k = c_k^T x_k (128x128 per image) and s_k = sum_px c_k, and the product with v
+//     becomes a per-image 1x1 "mix" matrix M_k = P_k Wv_k applied to x_k -- which rides along as one more
+//     K segment of the ResidualBlock's second 3x3 conv (gemm_slab.cu, mix segment), since
+//     x_1' = out_1 + x_2 + conv2(relu(conv1(x_2))).
+//   * c_k = clustering(LN(convf([x_s, x_other]))) is only used for G_k / s_k and for
+//     x_s' = unclustering([c_1, c_2]) + x_s, all of which can be formed while the c_k tile is still
+//     in shared memory.
+// bie_front_tc therefore reads x_1, x_2, x_s once and writes only x_s' plus small per-CTA partial
+// sums of G_k and s_k; att_fold turns those into M_k[b] and the per-image bias P_k bv_k.
+//
+// bie_front_tc, per 128-pixel tile (one CTA per SM, contiguous tile ranges, 384 threads):
+//   warp 0   TMA producer of the three input tiles (6 boxes [128 px x 64 ch], 96 KB)
+//   warp 1   TMA producer of the weight ring (5 x 16 KB; Wf 4 chunks, Wc 2, Wu 4 per tile, from L2)
+//   warps 2, 11  tcgen05.mma issuers (one thread each: accumulator A / B); warp 2 owns TMEM
+//   warps 3-10  epilogue: all eight work on ONE accumulator at a time (lane quarter x column half)
+// Two accumulators A and B ping-pong so the tensor core works on one k-path while the epilogue
+// warps post-process the other:
+//   MMA       Y1->A   Y2->B   C1->A      C2->B      att1,U(c1)->A    att2,s1,s2->B,U(c2)->A
+//   epilogue          LN(A)   LN(B)      C(A)       C(B)                               U(A)+s(B) [+flush]
+//   Y_k = [x_s, x_other] Wf^T ; LN = +bias, channel LayerNorm -> fp16 tile yn_k in smem (A operand of C_k)
+//   C_k = yn_k Wc^T ; C() = +bias, halo rows -> 0 -> fp16 tile c_k in smem
+//   att_k += c_k^T x_k (pixel-major operands, persistent TMEM accumulators over a run of tiles of one image)
+//   s_k = c_k^T 1 (an N=16 MMA against a block of ones: column 0 of row c is sum_px c_k[px, c])
+//   U = [c_1, c_2] Wu^T ; U() = +bias + x_s -> x_s' to HBM
+// Buffers: yn_1/c_1 own a tile; yn_2/c_2 overwrite the x_s tile (dead once Y2's MMAs retire).
+// TMEM: A, B (2 x 128 columns) + att_1, att_2 (2 x 128 columns) = 512.
+#include "gemm_epi.cuh"
+
+namespace bmc {
+namespace {
+
+constexpr int kFrontThreads = 384;
+constexpr int kTile = 128;
+constexpr int kHalfBytes = kTile * kChunkK * 2;      // one [128 x 64] fp16 box: 16 KB
+constexpr int kTensBytes = 2 * kHalfBytes;           // a 128-channel tile: 32 KB
+constexpr int kFrontWStages = 5;
+constexpr int kOnesBytes = 2048;                     // 16 pixel rows x 128 B of 1.0
+constexpr int kFrontSmem = 4 * kTensBytes + kFrontWStages * kHalfBytes + kOnesBytes + 1024;
+constexpr int kWChunksPerTile = 10;
+
+__host__ __device__ inline int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// Number of (cta, image) segments of CTAs < cta (all with full ranges): every CTA owns a contiguous
+// range of `tpc` tiles of the flattened (instance, image, tile) list and flushes one partial per
+// image it touches.  = cta + #image boundaries strictly inside those ranges.
+__host__ __device__ inline int segs_before(int cta, int tpc, int tpi, int lcm) {
+    if (cta == 0) return 0;
+    const int last = cta * tpc - 1;
+    return cta + last / tpi - last / lcm;
+}
+
+__device__ __forceinline__ void tmem_ld_32x32_x1(uint32_t taddr, uint32_t& v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+
+// fp16 row r, 32 channels starting at channel c*32, into a [128 x 128] tile stored as two
+// [128 x 64] SWIZZLE_128B boxes (the layout TMA writes and the UMMA descriptors read)
+__device__ __forceinline__ void store_tile_row32(uint8_t* tile, int r, int c, const float (&f)[32]) {
+    uint8_t* row = tile + (c >> 1) * kHalfBytes + r * 128;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int chunk = (c & 1) * 4 + u;
+        *reinterpret_cast<uint4*>(row + ((chunk ^ (r & 7)) << 4)) =
+            make_uint4(pack_act2(f[u * 8], f[u * 8 + 1]), pack_act2(f[u * 8 + 2], f[u * 8 + 3]),
+                       pack_act2(f[u * 8 + 4], f[u * 8 + 5]), pack_act2(f[u * 8 + 6], f[u * 8 + 7]));
+    }
+}
+
+#define FPROF(var, stmt) do { const long long _t = prof_on ? clock64() : 0; stmt; if (prof_on) var += clock64() - _t; } while (0)
+
+__global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_constant__ BieFrontParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_xs = smem;                              // x_s, then yn_2, then c_2
+    uint8_t* s_x1 = smem + kTensBytes;
+    uint8_t* s_x2 = smem + 2 * kTensBytes;
+    uint8_t* s_y = smem + 3 * kTensBytes;              // yn_1, then c_1, then store staging
+    uint8_t* s_w = smem + 4 * kTensBytes;
+    uint8_t* s_ones = s_w + kFrontWStages * kHalfBytes;
+
+    __shared__ uint64_t in_full, in_empty, w_full[kFrontWStages], w_empty[kFrontWStages];
+    __shared__ uint64_t acc_full[3], epi_done[2];      // per accumulator (A, B): strict ping-pong MMA <-> epilogue; [2] = U phase (both issuers)
+    __shared__ uint32_t tmem_base_s;
+    __shared__ __align__(16) float bias_f[128], bias_c[128], bias_u[128], gam_s[128], bet_s[128];
+    __shared__ float ln_sum[2][128], ln_var[2][128];
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tpi = p.tiles_per_img;
+    const int T0 = blockIdx.x * p.tiles_per_cta;
+    const int T1 = min(T0 + p.tiles_per_cta, p.total_tiles);
+    const bool prof_on = p.prof != nullptr;
+    const long long t_begin = prof_on ? clock64() : 0;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&in_full, 1); mbar_init(&in_empty, 2);
+        for (int s = 0; s < kFrontWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&epi_done[s], 8); }
+        mbar_init(&acc_full[2], 2);
+        mbar_fence_init();
+        tma_prefetch_desc(&p.map_act);
+        tma_prefetch_desc(&p.map_w);
+    }
+    if (warp == 2) tmem_alloc(&tmem_base_s, 512);
+    if (threadIdx.x < 128) {
+        const int t = threadIdx.x;
+        bias_f[t] = p.bf[t]; bias_c[t] = p.bc[t]; bias_u[t] = p.bu[t];
+        gam_s[t] = p.ln_gamma[t]; bet_s[t] = p.ln_beta[t];
+        const uint32_t one2 = pack_act2(1.f, 1.f);
+        *reinterpret_cast<uint4*>(s_ones + t * 16) = make_uint4(one2, one2, one2, one2);
+    }
+    fence_proxy_async_smem();                          // the ones block is read by the tensor core
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    const int B = p.g.B, R = p.g.R;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ input tiles
+        if (lane == 0) {
+            int lt = 0;
+            for (int T = T0; T < T1; ++T, ++lt) {
+                const int img = T / tpi, t = T - img * tpi;
+                const int inst = img / B, b = img - inst * B;
+                const int row0 = b * R + t * kTile;
+                if (lt > 0) mbar_wait(&in_empty, (lt - 1) & 1);
+                const BieInst& in = p.inst[inst];
+                mbar_expect_tx(&in_full, 3 * kTensBytes);
+                tma_load_2d(s_xs, &p.map_act, &in_full, 0, in.xs_row + row0);
+                tma_load_2d(s_xs + kHalfBytes, &p.map_act, &in_full, 64, in.xs_row + row0);
+                tma_load_2d(s_x1, &p.map_act, &in_full, 0, in.x1_row + row0);
+                tma_load_2d(s_x1 + kHalfBytes, &p.map_act, &in_full, 64, in.x1_row + row0);
+                tma_load_2d(s_x2, &p.map_act, &in_full, 0, in.x2_row + row0);
+                tma_load_2d(s_x2 + kHalfBytes, &p.map_act, &in_full, 64, in.x2_row + row0);
+                if (T + 1 < T1) {                  // start the HBM read of the next tile now; its smem buffers free up a tile later
+                    const int img2 = (T + 1) / tpi, t2 = (T + 1) - img2 * tpi;
+                    const int inst2 = img2 / B, b2 = img2 - inst2 * B;
+                    const int row2 = b2 * R + t2 * kTile;
+                    const BieInst& in2 = p.inst[inst2];
+                    for (int c0 = 0; c0 < 128; c0 += 64) {
+                        tma_prefetch_l2_2d(&p.map_act, c0, in2.xs_row + row2);
+                        tma_prefetch_l2_2d(&p.map_act, c0, in2.x1_row + row2);
+                        tma_prefetch_l2_2d(&p.map_act, c0, in2.x2_row + row2);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ weight ring: Wf[0..3], Wc[0..1], Wu[0..3] per tile
+        if (lane == 0) {
+            int wi = 0;
+            for (int T = T0; T < T1; ++T) {
+                for (int j = 0; j < kWChunksPerTile; ++j, ++wi) {
+                    const int st = wi % kFrontWStages;
+                    if (wi >= kFrontWStages) mbar_wait(&w_empty[st], ((wi / kFrontWStages) - 1) & 1);
+                    const int row = j < 4 ? p.wf_row + j * 128 : (j < 6 ? p.wc_row + (j - 4) * 128 : p.wu_row + (j - 6) * 128);
+                    mbar_expect_tx(&w_full[st], kHalfBytes);
+                    tma_load_2d(s_w + st * kHalfBytes, &p.map_w, &w_full[st], 0, row);
+                }
+            }
+        }
+    } else if (warp == 2 || warp == 11) {
+        // ------------------------------------------------------------ MMA issuers
+        // Two issuing threads (a lone one cannot keep the tensor pipe busy, see gemm_slab.cu): role 0 owns
+        // accumulator A (Y1, C1, att1, U), role 1 owns B (Y2, C2, att2, s).  Shared resources (weight
+        // stages, input tiles) are released by one tcgen05.commit from EACH thread (barrier count 2).
+        if (lane == 0) {
+            const int role = warp == 2 ? 0 : 1;
+            constexpr uint32_t idesc_k = umma_idesc_f16(128, 128, false, false);   // K-major A and B
+            constexpr uint32_t idesc_mn = umma_idesc_f16(128, 128, true, true);    // pixel-major A and B (K = pixels)
+            constexpr uint32_t idesc_s = umma_idesc_f16(128, 16, true, true);      // c_k^T . ones
+            constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+            const uint32_t accA = tmem_base, accB = tmem_base + 128, att0 = tmem_base + 256;
+            const uint32_t xs_lo = umma_desc_lo(smem_u32(s_xs), 16), x1_lo = umma_desc_lo(smem_u32(s_x1), 16),
+                           x2_lo = umma_desc_lo(smem_u32(s_x2), 16), y_lo = umma_desc_lo(smem_u32(s_y), 16);
+            // pixel-major views: 64-channel blocks kHalfBytes apart (LBO), 8-pixel groups 1024 B apart (SBO)
+            const uint32_t x_mn[2] = {umma_desc_lo(smem_u32(s_x1), kHalfBytes), umma_desc_lo(smem_u32(s_x2), kHalfBytes)};
+            const uint32_t c_mn[2] = {umma_desc_lo(smem_u32(s_y), kHalfBytes), umma_desc_lo(smem_u32(s_xs), kHalfBytes)};
+            const uint32_t ones_mn = umma_desc_lo(smem_u32(s_ones), kHalfBytes);
+            const uint32_t w_lo0 = umma_desc_lo(smem_u32(s_w), 16);
+            constexpr uint32_t half_units = kHalfBytes >> 4;
+            int wi = 0, lt = 0;
+            uint32_t epi_seen[2] = {0, 0};             // completions of epi_done[a] this thread has consumed or skipped
+            long long pw_in = 0, pw_w = 0, pw_epi = 0;
+            auto w_stage = [&](int j) -> uint32_t { return w_lo0 + ((wi + j) % kFrontWStages) * half_units; };
+            auto wait_w = [&](int j) {
+                FPROF(pw_w, mbar_wait(&w_full[(wi + j) % kFrontWStages], ((wi + j) / kFrontWStages) & 1));
+                tc_fence_after_sync();
+            };
+            auto free_w = [&](int j) { umma_commit(&w_empty[(wi + j) % kFrontWStages]); };
+            // wait for the n-th completion (0-based, counted from kernel start) of epi_done[a]
+            auto wait_epi_n = [&](int a, uint32_t n) {
+                FPROF(pw_epi, mbar_wait(&epi_done[a], n & 1));
+                tc_fence_after_sync();
+            };
+            auto mma4 = [&](uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t first_acc) {
+                umma_f16(acc, umma_desc(a_lo, hi), umma_desc(b_lo, hi), idesc_k, first_acc);
+                umma_f16(acc, umma_desc(a_lo + 2, hi), umma_desc(b_lo + 2, hi), idesc_k, 1u);
+                umma_f16(acc, umma_desc(a_lo + 4, hi), umma_desc(b_lo + 4, hi), idesc_k, 1u);
+                umma_f16(acc, umma_desc(a_lo + 6, hi), umma_desc(b_lo + 6, hi), idesc_k, 1u);
+            };
+            // epi_done[0] completes 3x per tile (LN(A), C(A), U), epi_done[1] 2x (LN(B), C(B))
+            for (int T = T0; T < T1; ++T, ++lt) {
+                const bool run_first = lt == 0 || (T % tpi) == 0;
+                const uint32_t eA = 3u * lt, eB = 2u * lt;      // completions before this tile
+                FPROF(pw_in, mbar_wait(&in_full, lt & 1));
+                tc_fence_after_sync();
+                if (lt > 0) wait_epi_n(0, eA - 1);              // U epilogue of the previous tile: A, B (s) and att are free
+                if (role == 0) {
+                    // ---- Y1 -> A = [xs, x2] Wf^T
+                    for (int j = 0; j < 4; ++j) {
+                        wait_w(j);
+                        mma4(accA, (j < 2 ? xs_lo : x2_lo) + (j & 1) * half_units, w_stage(j), j > 0);
+                        free_w(j);
+                    }
+                    wi += 4;
+                    umma_commit(&acc_full[0]);
+                    // ---- C1 -> A = yn1 Wc^T
+                    wait_epi_n(0, eA);                          // LN(A): yn1 in s_y, A drained
+                    for (int j = 0; j < 2; ++j) {
+                        wait_w(j);
+                        mma4(accA, y_lo + j * half_units, w_stage(j), j > 0);
+                        free_w(j);
+                    }
+                    wi += 2;
+                    umma_commit(&acc_full[0]);
+                    // ---- att1 += c1^T x1 ; U -> A = c1 Wu[0..1]^T
+                    wait_epi_n(0, eA + 1);                      // C(A): c1 in s_y, A drained
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)                 // one K=16 slice = 16 pixel rows = 2048 B
+                        umma_f16(att0, umma_desc(c_mn[0] + s * 128, hi), umma_desc(x_mn[0] + s * 128, hi), idesc_mn,
+                                 (run_first && s == 0) ? 0u : 1u);
+                    for (int j = 0; j < 2; ++j) {
+                        wait_w(j);
+                        mma4(accA, y_lo + j * half_units, w_stage(j), j > 0);
+                        free_w(j);
+                    }
+                    wi += 2;
+                    // ---- U += c2 Wu[2..3]^T
+                    wait_epi_n(1, eB + 1);                      // C(B): c2 in s_xs
+                    for (int j = 0; j < 2; ++j) {
+                        wait_w(j);
+                        mma4(accA, xs_lo + j * half_units, w_stage(j), 1u);
+                        free_w(j);
+                    }
+                    wi += 2;
+                } else {
+                    // ---- Y2 -> B = [xs, x1] Wf^T
+                    for (int j = 0; j < 4; ++j) {
+                        wait_w(j);
+                        mma4(accB, (j < 2 ? xs_lo : x1_lo) + (j & 1) * half_units, w_stage(j), j > 0);
+                        free_w(j);
+                    }
+                    wi += 4;
+                    umma_commit(&acc_full[1]);
+                    // ---- C2 -> B = yn2 Wc^T
+                    wait_epi_n(1, eB);                          // LN(B): yn2 in s_xs, B drained
+                    for (int j = 0; j < 2; ++j) {
+                        wait_w(j);
+                        mma4(accB, xs_lo + j * half_units, w_stage(j), j > 0);
+                        free_w(j);
+                    }
+                    wi += 2;
+                    umma_commit(&acc_full[1]);
+                    // ---- att2 += c2^T x2 ; s_k = c_k^T 1 -> B[16k .. 16k+15]
+                    wait_epi_n(1, eB + 1);                      // C(B): c2 in s_xs, B drained
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        umma_f16(att0 + 128, umma_desc(c_mn[1] + s * 128, hi), umma_desc(x_mn[1] + s * 128, hi), idesc_mn,
+                                 (run_first && s == 0) ? 0u : 1u);
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        umma_f16(accB + 16, umma_desc(c_mn[1] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
+                    wait_epi_n(0, eA + 1);                      // C(A): c1 in s_y
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        umma_f16(accB, umma_desc(c_mn[0] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
+                    for (int j = 0; j < 4; ++j) free_w(j);      // the Wu stages: this thread's share of the release
+                    wi += 4;
+                }
+                umma_commit(&in_empty);            // inputs and c tiles are consumed once both threads' MMAs retire
+                umma_commit(&acc_full[2]);         // U, s, att complete (both threads)
+            }
+            if (prof_on && role == 0) {
+                long long* o = p.prof + blockIdx.x * 16;
+                o[0] = pw_in; o[1] = pw_w; o[2] = pw_epi; o[3] = clock64() - t_begin; o[4] = lt;
+            }
+            (void)epi_seen;
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue (warps 3..10)
+        const int e = warp - 3;
+        const int ch = e >> 2;                     // column half: channels [64 ch, 64 ch + 64)
+        const int q = warp & 3;                    // TMEM lane quarter this warp may read
+        const int r = q * 32 + lane;               // row of the tile
+        const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+        const int tt = threadIdx.x - 96;           // 0..255
+        uint32_t acc_uses[3] = {0, 0, 0};
+        float s_run = 0.f;                         // running sum_px c_k[px, c] for k = ch, c = r
+        int slot = segs_before(blockIdx.x, p.tiles_per_cta, tpi, p.lcm);
+        long long pe_wait = 0, pe_ln = 0, pe_c = 0, pe_u = 0, pe_flush = 0;
+        auto wait_acc = [&](int a) {
+            FPROF(pe_wait, mbar_wait(&acc_full[a], acc_uses[a] & 1));
+            ++acc_uses[a];
+            tc_fence_after_sync();
+        };
+        auto phase_done = [&](int a, bool wrote_smem) {
+            if (wrote_smem) fence_proxy_async_smem();
+            tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&epi_done[a]);
+        };
+        for (int T = T0; T < T1; ++T) {
+            const int img = T / tpi, t = T - img * tpi;
+            const int inst = img / B, b = img - inst * B;
+            const int r_img = t * kTile + r;
+            int yy, xx;
+            const bool valid = p.g.interior(r_img, yy, xx);
+            const bool run_last = (T + 1 == T1) || ((T + 1) % tpi == 0);
+            // ---- LN(A), LN(B): yn_k = LayerNorm(Y_k + bf)  (submodules.py:63-64, 127-139)
+#pragma unroll 1
+            for (int a = 0; a < 2; ++a) {
+                wait_acc(a);
+                const long long _tp = prof_on ? clock64() : 0;
+                const uint32_t trow = tmem_base + a * 128 + lane_off + ch * 64;
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(trow, v0);
+                tmem_ld_32x32(trow + 32, v1);
+                tmem_ld_wait();
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float x0 = __uint_as_float(v0[j]) + bias_f[ch * 64 + j];
+                    const float x1 = __uint_as_float(v1[j]) + bias_f[ch * 64 + 32 + j];
+                    v0[j] = __float_as_uint(x0); v1[j] = __float_as_uint(x1);
+                    sum += x0 + x1;
+                }
+                ln_sum[ch][r] = sum;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float mu = (sum + ln_sum[ch ^ 1][r]) * (1.f / 128.f);
+                float var = 0.f;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float d0 = __uint_as_float(v0[j]) - mu, d1 = __uint_as_float(v1[j]) - mu;
+                    var += d0 * d0 + d1 * d1;
+                }
+                ln_var[ch][r] = var;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                const float rstd = 1.f / sqrtf((var + ln_var[ch ^ 1][r]) * (1.f / 128.f) + p.ln_eps);
+                uint8_t* dst = a == 0 ? s_y : s_xs;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    f[j] = gam_s[ch * 64 + j] * ((__uint_as_float(v0[j]) - mu) * rstd) + bet_s[ch * 64 + j];
+                store_tile_row32(dst, r, ch * 2, f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    f[j] = gam_s[ch * 64 + 32 + j] * ((__uint_as_float(v1[j]) - mu) * rstd) + bet_s[ch * 64 + 32 + j];
+                store_tile_row32(dst, r, ch * 2 + 1, f);
+                phase_done(a, true);
+                if (prof_on) pe_ln += clock64() - _tp;
+            }
+            // ---- C(A), C(B): c_k = C_k + bc, halo rows zero  (`clustering`, submodules.py:63-64)
+#pragma unroll 1
+            for (int a = 0; a < 2; ++a) {
+                wait_acc(a);
+                const long long _tp = prof_on ? clock64() : 0;
+                const uint32_t trow = tmem_base + a * 128 + lane_off + ch * 64;
+                uint32_t v0[32], v1[32];
+                tmem_ld_32x32(trow, v0);
+                tmem_ld_32x32(trow + 32, v1);
+                tmem_ld_wait();
+                uint8_t* dst = a == 0 ? s_y : s_xs;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v0[j]) + bias_c[ch * 64 + j] : 0.f;
+                store_tile_row32(dst, r, ch * 2, f);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v1[j]) + bias_c[ch * 64 + 32 + j] : 0.f;
+                store_tile_row32(dst, r, ch * 2 + 1, f);
+                phase_done(a, true);
+                if (prof_on) pe_c += clock64() - _tp;
+            }
+            // ---- U(A): x_s' = U + bu + x_s  (submodules.py:75); s_k from B
+            {
+                const BieInst& in = p.inst[inst];
+                const long m_warp = (long)b * R + t * kTile + q * 32;      // first row of this warp's 32-row block
+                const act_t* res = p.act_base + ((long)in.xs_row + m_warp) * 128;
+                act_t* out = p.out_base + ((long)in.out_row + m_warp) * 128;
+                const int crow = lane >> 2, cchunk = lane & 3;             // coalesced mapping: row crow + 8i, 16-byte piece cchunk
+                // residual rows are fetched before the accumulator is awaited (latency off the critical path)
+                uint4 rv[2][4];
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        rv[cc][i] = *reinterpret_cast<const uint4*>(res + (long)(crow + 8 * i) * 128 + (ch * 2 + cc) * 32 + cchunk * 8);
+                wait_acc(2);
+                const long long _tp = prof_on ? clock64() : 0;
+                uint8_t* stage = s_y + e * 2048;                           // c_1 is dead: the MMAs that read it have retired
+                const uint32_t trow = tmem_base + lane_off + ch * 64;
+                uint32_t v0[32], v1[32], sv;
+                tmem_ld_32x32(trow, v0);
+                tmem_ld_32x32(trow + 32, v1);
+                tmem_ld_32x32_x1(tmem_base + 128 + lane_off + 16 * ch, sv);
+                tmem_ld_wait();
+                s_run += __uint_as_float(sv);
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c = ch * 2 + cc;
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(cc == 0 ? v0[j] : v1[j]) + bias_u[c * 32 + j];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + stage_off(crow + 8 * i, cchunk)) = rv[cc][i];
+                    __syncwarp();
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const uint4 x = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
+                        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                        for (int k2 = 0; k2 < 4; ++k2) {
+                            const float2 t2 = unpack_act2(w[k2]);
+                            f[u * 8 + k2 * 2] += t2.x;
+                            f[u * 8 + k2 * 2 + 1] += t2.y;
+                        }
+                    }
+                    __syncwarp();
+                    if (!valid) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
+                            make_uint4(pack_act2(f[u * 8], f[u * 8 + 1]), pack_act2(f[u * 8 + 2], f[u * 8 + 3]),
+                                       pack_act2(f[u * 8 + 4], f[u * 8 + 5]), pack_act2(f[u * 8 + 6], f[u * 8 + 7]));
+                    __syncwarp();
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = crow + 8 * i;
+                        *reinterpret_cast<uint4*>(out + (long)row * 128 + c * 32 + cchunk * 8) =
+                            *reinterpret_cast<const uint4*>(stage + stage_off(row, cchunk));
+                    }
+                    __syncwarp();
+                }
+                if (prof_on) pe_u += clock64() - _tp;
+            }
+            if (run_last) {
+                // end of a run of tiles of one image: att_k (complete -- the commit behind acc_full covers
+                // its MMAs) and s_k go to this CTA's next partial slot.  Each warp transposes its
+                // [32 rows x 32 cols] fp32 blocks through a private 4 KB tile so rows leave as full lines.
+                const long long _tp = prof_on ? clock64() : 0;
+                asm volatile("bar.sync 1, 256;" ::: "memory");             // every warp is done with its store staging
+                float* tile = reinterpret_cast<float*>(s_y + e * 4096);
+#pragma unroll 1
+                for (int kc = 0; kc < 4; ++kc) {
+                    const int k = kc >> 1, c = ch * 2 + (kc & 1);          // att_k, columns [32 c, 32 c + 32)
+                    uint32_t v[32];
+                    tmem_ld_32x32(tmem_base + 256 + k * 128 + lane_off + c * 32, v);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        *reinterpret_cast<uint4*>(tile + lane * 32 + ((u ^ (lane & 7)) << 2)) =
+                            make_uint4(v[u * 4], v[u * 4 + 1], v[u * 4 + 2], v[u * 4 + 3]);
+                    __syncwarp();
+                    float* gp = p.g_partial + (((long)slot * 2 + k) * 128 + q * 32) * 128 + c * 32;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = (lane >> 3) + 4 * i, u = lane & 7;
+                        *reinterpret_cast<uint4*>(gp + (long)row * 128 + u * 4) =
+                            *reinterpret_cast<const uint4*>(tile + row * 32 + ((u ^ (row & 7)) << 2));
+                    }
+                    __syncwarp();
+                }
+                p.s_partial[(long)slot * 256 + ch * 128 + r] = s_run;
+                s_run = 0.f;
+                ++slot;
+                if (prof_on) pe_flush += clock64() - _tp;
+            }
+            phase_done(0, false);
+        }
+        if (prof_on && tt == 0) {
+            long long* o = p.prof + blockIdx.x * 16;
+            o[8] = pe_wait; o[9] = pe_ln; o[10] = pe_c; o[11] = pe_u; o[12] = pe_flush; o[13] = clock64() - t_begin;
+        }
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// att_fold: one CTA per (instance, image, k, block of 32 rows c) -- rows are independent.
+//   att = scale * (G Wv^T + s bv^T)     (== centres . v^T * nf^-0.5, submodules.py:69-70)
+//   P   = softmax(att, -1)              (submodules.py:72-73)
+//   M   = P Wv  -> fp16 chunk-major [2][128][64] (the mix segment's B operand),  bias' = P bv
+// 128 threads: thread (rg = tid / 16, cg = tid % 16) owns rows 4 rg .. 4 rg + 3 and 8 columns
+// (4 x 8 register tile: 12 shared-memory float4 loads per 128 FMAs).
+constexpr int kFoldRows = 32;
+constexpr int kFoldLd = 132;              // Wv row pitch in floats: 16-byte aligned, rows 4 banks apart
+__global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
+    extern __shared__ __align__(16) float fsm[];
+    float* Wv = fsm;                                  // [128][132]: Wv[c'][i]
+    float* Gs = fsm + 128 * kFoldLd;                  // [32][128]: G rows, later P rows
+    __shared__ float s_bv[128], s_s[kFoldRows];
+    constexpr int kBlocks = 128 / kFoldRows;
+    const int rb = blockIdx.x % kBlocks;
+    const int k = (blockIdx.x / kBlocks) & 1;
+    const int img = blockIdx.x / (2 * kBlocks);
+    const int inst = img / p.B, b = img - inst * p.B;
+    const int tid = threadIdx.x;
+    // partial slots of this image: contiguous, one per CTA of bie_front_tc that touched it
+    const int tpc = p.tiles_per_cta, tpi = p.tiles_per_img;
+    const int c_a = (img * tpi) / tpc, c_b = ((img + 1) * tpi - 1) / tpc;
+    const int slot_a = segs_before(c_a, tpc, tpi, p.lcm) + (img - (c_a * tpc) / tpi);
+    const int n_slots = c_b - c_a + 1;
+    // All global reads are issued up front (they are pure latency: ~10 dependent L2 round trips otherwise).
+    // Wv[c'][i] from the chunk-major fp16 matrix: row wv_row + (i/64)*128 + c', column i%64 (8 values per load)
+    uint4 wraw[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int idx = tid + 128 * u, cp = idx >> 4, i8 = (idx & 15) * 8;
+        wraw[u] = *reinterpret_cast<const uint4*>(p.w_base + ((long)p.wv_row[k] + (i8 >> 6) * 128 + cp) * 64 + (i8 & 63));
+    }
+    float s_val = 0.f;
+    if (tid < kFoldRows) {
+        float sv[4] = {0.f, 0.f, 0.f, 0.f};
+        const float* __restrict__ sp = p.s_partial + (long)slot_a * 256 + k * 128 + rb * kFoldRows + tid;
+        for (int s = 0; s < n_slots; s += 4) {
+#pragma unroll
+            for (int d = 0; d < 4; ++d) sv[d] += (s + d < n_slots) ? sp[(long)(s + d) * 256] : 0.f;
+        }
+        s_val = ((sv[0] + sv[1]) + (sv[2] + sv[3]));
+    }
+    {   // G rows summed over the partial slots in a fixed order; 8 positions per thread, 3 slots in flight
+        const float* __restrict__ gp = p.g_partial + (((long)slot_a * 2 + k) * 128 + rb * kFoldRows) * 128;
+        float4 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n_slots; s += 3) {
+            float4 t[3][8];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    t[d][u] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(gp + (long)(s + d) * 2 * 128 * 128 + (tid + 128 * u) * 4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[u].x += t[d][u].x; a[u].y += t[d][u].y; a[u].z += t[d][u].z; a[u].w += t[d][u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(Gs + (tid + 128 * u) * 4) = a[u];
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+        const int idx = tid + 128 * u, cp = idx >> 4, i8 = (idx & 15) * 8;
+        const float2 a = unpack_act2(wraw[u].x), b2 = unpack_act2(wraw[u].y), c2 = unpack_act2(wraw[u].z), d = unpack_act2(wraw[u].w);
+        float* dst = Wv + cp * kFoldLd + i8;
+        *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b2.x, b2.y);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(c2.x, c2.y, d.x, d.y);
+    }
+    s_bv[tid] = p.bv[k][tid];
+    if (tid < kFoldRows) s_s[tid] = s_val;
+    __syncthreads();
+    const int rg = tid >> 4, cg = tid & 15;
+    // logits: rows 4 rg + a, columns c' = cg + 16 j
+    float acc[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
+    for (int i = 0; i < 128; i += 4) {
+        float4 gv[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) gv[a] = *reinterpret_cast<const float4*>(Gs + (rg * 4 + a) * 128 + i);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float4 w = *reinterpret_cast<const float4*>(Wv + (cg + 16 * j) * kFoldLd + i);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) acc[a][j] += gv[a].x * w.x + gv[a].y * w.y + gv[a].z * w.z + gv[a].w * w.w;
+        }
+    }
+    float bsum[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const float sc = s_s[rg * 4 + a];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc[a][j] = (acc[a][j] + sc * s_bv[cg + 16 * j]) * p.scale;
+            mx = fmaxf(mx, acc[a][j]);
+        }
+        for (int o = 8; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[a][j] = expf(acc[a][j] - mx); sum += acc[a][j]; }
+        for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        float bs = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { acc[a][j] *= inv; bs += acc[a][j] * s_bv[cg + 16 * j]; }
+        for (int o = 8; o; o >>= 1) bs += __shfl_xor_sync(0xffffffffu, bs, o);
+        bsum[a] = bs;
+    }
+    __syncthreads();                                   // every thread is done reading the G rows
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) Gs[(rg * 4 + a) * 128 + cg + 16 * j] = acc[a][j];       // P
+    __syncthreads();
+    // M[c][i] = sum_c' P[c][c'] Wv[c'][i] for i = cg*4 + 64 u + (0..3)
+    float4 m[4][2];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { m[a][0] = make_float4(0.f, 0.f, 0.f, 0.f); m[a][1] = m[a][0]; }
+    for (int cp = 0; cp < 128; cp += 4) {
+        float4 pr[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) pr[a] = *reinterpret_cast<const float4*>(Gs + (rg * 4 + a) * 128 + cp);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const float4 w = *reinterpret_cast<const float4*>(Wv + (cp + d) * kFoldLd + cg * 4 + 64 * u);
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const float pv = d == 0 ? pr[a].x : (d == 1 ? pr[a].y : (d == 2 ? pr[a].z : pr[a].w));
+                    m[a][u].x += pv * w.x; m[a][u].y += pv * w.y; m[a][u].z += pv * w.z; m[a][u].w += pv * w.w;
+                }
+            }
+        }
+    }
+    const int pair = inst * 2 + k;
+    act_t* mb = p.m_base + ((long)pair * p.B + b) * 256 * 64;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int c = rb * kFoldRows + rg * 4 + a;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            uint2 o2;
+            o2.x = pack_act2(m[a][u].x, m[a][u].y);
+            o2.y = pack_act2(m[a][u].z, m[a][u].w);
+            *reinterpret_cast<uint2*>(mb + (u * 128 + c) * 64 + cg * 4) = o2;      // i = cg*4 + 64 u: chunk u, column cg*4
+        }
+        if (cg == 0) p.bias_img[((long)pair * p.B + b) * 128 + c] = bsum[a];
+    }
+}
+
+}  // namespace
+
+int bie_front_grid(int total_tiles) { return total_tiles < sm_count() ? total_tiles : sm_count(); }
+
+int bie_front_lcm(int tiles_per_cta, int tiles_per_img) {
+    return tiles_per_cta / gcd_i(tiles_per_cta, tiles_per_img) * tiles_per_img;
+}
+
+// Upper bound on the partial slots bie_front_tc writes: one per (CTA, image it touches).
+int bie_front_slots(int total_tiles, int tiles_per_img) {
+    const int grid = bie_front_grid(total_tiles);
+    const int tpc = (total_tiles + grid - 1) / grid;
+    int n = 0;
+    for (int c = 0; c < grid; ++c) {
+        const int t0 = c * tpc, t1 = t0 + tpc < total_tiles ? t0 + tpc : total_tiles;
+        if (t0 >= t1) break;
+        n += (t1 - 1) / tiles_per_img - t0 / tiles_per_img + 1;
+    }
+    return n;
+}
+
+int launch_bie_front(const BieFrontParams& p, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        BMC_CUDA(cudaFuncSetAttribute(bie_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmem));
+        configured = true;
+    }
+    const int grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+    static long long* prof = nullptr;
+    static int prof_init = 0, dumped = 0;
+    if (!prof_init) {
+        prof_init = 1;
+        if (getenv("BMC_FRONT_PROF")) { cudaMalloc(&prof, 148 * 16 * sizeof(long long)); cudaMemset(prof, 0, 148 * 16 * sizeof(long long)); }
+    }
+    BieFrontParams q = p;
+    q.prof = prof;
+    bie_front_tc<<<grid, kFrontThreads, kFrontSmem, st>>>(q);
+    BMC_CUDA(cudaGetLastError());
+    if (prof && dumped++ == 7) {           // a warm launch
+        cudaStreamSynchronize(st);
+        long long h[148 * 16];
+        cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
+        for (int c : {0, 1, 73, 147}) {
+            const long long* o = h + c * 16;
+            printf("frontprof cta %3d: tiles %lld | MMA wait_in %lld wait_w %lld wait_epi %lld of %lld | EPI wait_acc %lld ln %lld c %lld u %lld flush %lld of %lld\n",
+                   c, o[4], o[0], o[1], o[2], o[3], o[8], o[9], o[10], o[11], o[12], o[13]);
+        }
+    }
+    return BMC_OK;
+}
+
+int launch_att_fold(const FoldParams& p, cudaStream_t st) {
+    const int smem = (128 * kFoldLd + kFoldRows * 128) * (int)sizeof(float);
+    static bool configured = false;
+    if (!configured) {
+        BMC_CUDA(cudaFuncSetAttribute(att_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured = true;
+    }
+    att_fold<<<p.n_inst * p.B * 2 * (128 / kFoldRows), 128, smem, st>>>(p);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+}  // namespace bmc

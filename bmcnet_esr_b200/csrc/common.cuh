@@ -154,6 +154,13 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* map, uin
         : "memory");
 }
 
+// Pull a 2-D box into L2 only (no shared-memory destination, no barrier): used to start the HBM read
+// of a tile whose shared-memory buffer is still busy.
+__device__ __forceinline__ void tma_prefetch_l2_2d(const void* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
 // ---------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(

@@ -47,6 +47,14 @@ struct GemmJobDev {
     const float* ln_gamma;
     const float* ln_beta;
     float ln_eps;
+    // centre-tap-only ("1x1") segments of a 3x3 launch (GemmParams::tap1_mask), each with its own weights:
+    //   * the per-image mix matrix M_k[b] of the fused BIE (out_k = softmax(att_k) @ v_k = M_k[b] . x_k,
+    //     bie_fused.cu, submodules.py:72-77): t1_img_stride != 0;
+    //   * the identity matrix: the residual add `identity + out` (submodules.py:35) done by the tensor core
+    //     (1.0 * x accumulates exactly in fp32), which keeps the epilogue free of a second global read.
+    int t1_map[kMaxSeg];       // TMA map of the segment's weights [.][64], chunk-major [chunks][128][64]
+    int t1_row[kMaxSeg], t1_img_stride[kMaxSeg];
+    const float* bias_img;     // per-image extra bias [B][128] added to `bias`, or NULL
 };
 
 struct alignas(64) GemmParams {
@@ -58,12 +66,15 @@ struct alignas(64) GemmParams {
     int n_taps;
     int tap_off[9];            // row shift of each tap: dy*Wp + dx
     int n;                     // output channels: 128 or 32
+    int tap1_mask;             // bit s: segment s contributes its centre tap only, with weights from GemmJobDev::t1_*
     Geom g;
     int tiles_per_img;         // R / 128
     // slab kernel (gemm_slab.cu); filled in by its launcher
-    int slab_lead, slab_boxes, tiles_per_job, bo_mode;
-    int per_image;             // tiles never straddle images (per-image dynamic weights); tiles_per_img256 each
-    int tiles_per_img256;
+    int slab_lead, slab_boxes, bo_mode;
+    int per_image;             // tiles never straddle images (per-image weights)
+    // tile schedule: `n_full` 256-row tiles, then `n_half` 128-row tiles (the odd half at the end of every
+    // image in per-image mode), the halves going to the CTAs that got one full tile less
+    int n_full, n_half, full_per_img;
     long long* prof;           // optional per-CTA cycle counters (tools/gpu_diag.py slabprof), else NULL
 };
 
@@ -89,6 +100,43 @@ struct SoftmaxParams {
     int w_row_base[kMaxPairs];             // chunk-major block [2][128][64] starting at row
     int w_img_stride;                      // w_row_base[pair] + b * w_img_stride
 };
+
+// Fused 1x1 / attention section of BIE.forward (bie_fused.cu; submodules.py:63-75).
+constexpr int kMaxInst = 2;
+struct BieInst {
+    int x1_row, x2_row, xs_row, out_row;   // first arena row of x_1, x_2, x_s and of the x_s_ output
+};
+struct alignas(64) BieFrontParams {
+    CUtensorMap map_act;                   // activation arena, box [128 rows][64 ch]
+    CUtensorMap map_w;                     // static weights, box [128 rows][64]
+    BieInst inst[kMaxInst];
+    int n_inst;
+    int wf_row, wc_row, wu_row;            // first rows of convf (4 chunks), clustering (2), unclustering (4)
+    const float* bf; const float* bc; const float* bu;
+    const float* ln_gamma; const float* ln_beta; float ln_eps;
+    const act_t* act_base;                 // arena base (residual x_s rows / output rows)
+    act_t* out_base;
+    float* g_partial;                      // [slot][2][128][128]: sum_px c_k[px,c] * x_k[px,i]
+    float* s_partial;                      // [slot][2][128]:      sum_px c_k[px,c]
+    Geom g;
+    int tiles_per_img, total_tiles, tiles_per_cta, lcm;      // lcm(tiles_per_cta, tiles_per_img): slot numbering
+    long long* prof;                       // optional per-CTA cycle counters (BMC_FRONT_PROF), else NULL
+};
+struct FoldParams {
+    const float* g_partial; const float* s_partial;
+    int n_inst, B, tiles_per_img, tiles_per_cta, total_tiles, lcm;
+    const act_t* w_base;                   // static weight matrix [rows][64]
+    int wv_row[2];                         // first row of v1 / v2 (2 chunks of 128 rows each)
+    const float* bv[2];
+    float scale;
+    act_t* m_base;                         // per-image matrices: rows pair*B*256 + b*256 + chunk*128 + c, pair = inst*2 + k
+    float* bias_img;                       // [pair][B][128]
+};
+int launch_bie_front(const BieFrontParams& p, cudaStream_t st);
+int launch_att_fold(const FoldParams& p, cudaStream_t st);
+int bie_front_grid(int total_tiles);
+int bie_front_slots(int total_tiles, int tiles_per_img);
+int bie_front_lcm(int tiles_per_cta, int tiles_per_img);
 
 // Launchers (host).  `impl`: 0 = tcgen05/TMA (slab kernel when it applies, else the per-tap
 // kernel), 1 = SIMT cross-check, 2 = force the per-tap tcgen05 kernel.
@@ -123,6 +171,7 @@ struct EmitParams {
     Geom g;
 };
 int launch_emit(const EmitParams& p, cudaStream_t st);
+int launch_fill_identity(act_t* dst, cudaStream_t st);      // [2][128][64] chunk-major 128x128 identity
 int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out,
                          int n_out_pad, int K, act_t* dst, int w_rows, int w_row_base,
                          cudaStream_t st);

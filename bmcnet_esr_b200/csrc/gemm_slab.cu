@@ -49,8 +49,6 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
     __shared__ __align__(16) float bias_s[2][N];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_job = p.tiles_per_job;
-    const int total_tiles = tiles_per_job * p.n_jobs;
     const long rows_total = p.g.rows();
     const int n_taps = p.n_taps;
 
@@ -59,28 +57,54 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
     long long w0 = 0, w1 = 0, w2 = 0;                  // role-specific wait buckets
     // (segment, chunk) steps of one tile and where their weights start
     int a_steps = 0;
-    int as_seg[kMaxASteps], as_chunk[kMaxASteps], as_k0[kMaxASteps], as_cs[kMaxASteps];
+    int as_seg[kMaxASteps], as_chunk[kMaxASteps], as_k0[kMaxASteps], as_cs[kMaxASteps], as_taps[kMaxASteps];
+    const int tap1_mask = p.tap1_mask;                  // centre-tap-only segments (per-image mix matrix / identity)
+    int steps = 0;                                      // K steps (one tap of one chunk) per tile
     {
         int seg_chunk0 = 0;
         for (int s = 0; s < p.n_seg; ++s) {
+            const int taps_s = (tap1_mask >> s) & 1 ? 1 : n_taps;
             for (int c = 0; c < p.chunks[s]; ++c, ++a_steps) {
                 as_seg[a_steps] = s; as_chunk[a_steps] = c; as_k0[a_steps] = seg_chunk0 + c; as_cs[a_steps] = p.chunks[s];
+                as_taps[a_steps] = taps_s;
+                steps += taps_s;
             }
-            seg_chunk0 += n_taps * p.chunks[s];
+            if (!((tap1_mask >> s) & 1)) seg_chunk0 += n_taps * p.chunks[s];
         }
     }
-    // tile -> (first row, one-past-last storable row, image for per-image weights)
-    auto tile_rows = [&](int tile, long& m0, long& m_end, int& img) {
-        const int rem = tile % tiles_per_job;
-        if (p.per_image) {
-            img = rem / p.tiles_per_img256;
-            m0 = (long)img * p.g.R + (long)(rem - img * p.tiles_per_img256) * kBM;
-            m_end = (long)(img + 1) * p.g.R;
+    // This CTA's tile sequence: its share of the full (256-row) tiles round-robin, then -- in per-image
+    // mode, where every image ends in a 128-row half tile -- its share of the half tiles, dealt to the
+    // CTAs that got one full tile less.  li-th tile -> (job, first row, one-past-last storable row, image, half)
+    const int G = gridDim.x, cta = blockIdx.x;
+    const int n_full_mine = p.n_full > cta ? (p.n_full - cta + G - 1) / G : 0;
+    const int first_light = p.n_full % G, n_light = G - first_light;
+    const int n_half_mine = (cta >= first_light && p.n_half > cta - first_light) ? (p.n_half - (cta - first_light) + n_light - 1) / n_light : 0;
+    const int n_mine = n_full_mine + n_half_mine;
+    auto tile_at = [&](int li, int& job, long& m0, long& m_end, int& img, bool& half) {
+        if (li < n_full_mine) {
+            const int t = cta + li * G;
+            half = false;
+            if (p.per_image) {
+                const int per_job = p.g.B * p.full_per_img;
+                job = t / per_job;
+                const int rem = t - job * per_job;
+                img = rem / p.full_per_img;
+                m0 = (long)img * p.g.R + (long)(rem - img * p.full_per_img) * kBM;
+                m_end = (long)(img + 1) * p.g.R;
+            } else {
+                const int per_job = p.n_full / p.n_jobs;
+                job = t / per_job;
+                img = 0; m0 = (long)(t - job * per_job) * kBM; m_end = rows_total;
+            }
         } else {
-            img = 0; m0 = (long)rem * kBM; m_end = rows_total;
+            const int h = (cta - first_light) + (li - n_full_mine) * n_light;
+            half = true;
+            job = h / p.g.B;
+            img = h - job * p.g.B;
+            m0 = (long)img * p.g.R + (long)p.full_per_img * kBM;
+            m_end = (long)(img + 1) * p.g.R;
         }
     };
-    const int steps = a_steps * n_taps;                 // K steps (one tap of one chunk) per tile
     const int groups = (steps + kWGroup - 1) / kWGroup; // weight stages per tile
 
     if (threadIdx.x == 0) {
@@ -100,10 +124,10 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
         // ------------------------------------------------------------ activation slabs
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const GemmJobDev& job = p.jobs[tile / tiles_per_job];
-                long m0l, m_end; int img;
-                tile_rows(tile, m0l, m_end, img);
+            for (int li = 0; li < n_mine; ++li) {
+                long m0l, m_end; int img, ji; bool half;
+                tile_at(li, ji, m0l, m_end, img, half);
+                const GemmJobDev& job = p.jobs[ji];
                 const int m0 = (int)m0l;
                 for (int as = 0; as < a_steps; ++as, ++it) {
                     const int s = as_seg[as];
@@ -112,9 +136,11 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     uint8_t* dst = smem + st * slab_bytes;
                     if ((p.bo_mode & 1) && it >= kSlabStages) { mbar_arrive(&a_full[st]); continue; }   // experiment: no TMA
                     const CUtensorMap* map = &p.maps[job.a_map64[s]];
-                    const int row0 = job.a_row_base[s] + m0 - p.slab_lead;
-                    mbar_expect_tx(&a_full[st], slab_bytes);
-                    for (int b = 0; b < p.slab_boxes; ++b)
+                    const bool mix = (tap1_mask >> s) & 1;   // centre tap only: just the tile's own 256 rows
+                    const int row0 = job.a_row_base[s] + m0 - (mix ? 0 : p.slab_lead);
+                    const int boxes = mix ? kBM / kBoxRows : p.slab_boxes;
+                    mbar_expect_tx(&a_full[st], boxes * kBoxBytes);
+                    for (int b = 0; b < boxes; ++b)
                         tma_load_2d(dst + b * kBoxBytes, map, &a_full[st], job.a_col_base[s] + as_chunk[as] * kChunkK,
                                     row0 + b * kBoxRows);
                 }
@@ -125,11 +151,11 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
         // ------------------------------------------------------------ weight tiles, kWGroup taps per stage
         if (lane == 0) {
             int gi = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const GemmJobDev& job = p.jobs[tile / tiles_per_job];
+            for (int li = 0; li < n_mine; ++li) {
+                long m0l, m_end; int img, ji; bool half;
+                tile_at(li, ji, m0l, m_end, img, half);
+                const GemmJobDev& job = p.jobs[ji];
                 const CUtensorMap* map = &p.maps[job.w_map];
-                long m0l, m_end; int img;
-                tile_rows(tile, m0l, m_end, img);
                 const int w_row0 = job.w_row_base + img * job.w_img_stride;
                 int as = 0, tap = 0;
                 for (int g = 0; g < groups; ++g, ++gi) {
@@ -138,15 +164,21 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     const int cnt = min(kWGroup, steps - g * kWGroup);
                     if ((p.bo_mode & 1) && gi >= kWStages) {                               // experiment: no TMA
                         mbar_arrive(&w_full[st]);
-                        for (int j = 0; j < cnt; ++j) if (++tap == n_taps) { tap = 0; ++as; }
+                        for (int j = 0; j < cnt; ++j) if (++tap == as_taps[as]) { tap = 0; ++as; }
                         continue;
                     }
                     mbar_expect_tx(&w_full[st], cnt * kWBytes);
                     for (int j = 0; j < cnt; ++j) {
-                        const int kchunk = as_k0[as] + tap * as_cs[as];                    // K order (seg, tap, chunk)
-                        tma_load_2d(smem_w + st * kWStageBytes + j * kWBytes, map, &w_full[st], 0,
-                                    kchunk * job.w_rows + w_row0);
-                        if (++tap == n_taps) { tap = 0; ++as; }
+                        const int sg = as_seg[as];
+                        if ((tap1_mask >> sg) & 1) {                                       // own weights, chunk-major [chunks][128][64]
+                            tma_load_2d(smem_w + st * kWStageBytes + j * kWBytes, &p.maps[job.t1_map[sg]], &w_full[st], 0,
+                                        job.t1_row[sg] + img * job.t1_img_stride[sg] + as_chunk[as] * 128);
+                        } else {
+                            const int kchunk = as_k0[as] + tap * as_cs[as];                // K order (seg, tap, chunk)
+                            tma_load_2d(smem_w + st * kWStageBytes + j * kWBytes, map, &w_full[st], 0,
+                                        kchunk * job.w_rows + w_row0);
+                        }
+                        if (++tap == as_taps[as]) { tap = 0; ++as; }
                     }
                 }
             }
@@ -172,13 +204,19 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             const uint32_t w_lo0 = umma_desc_lo(smem_u32(smem_w), 16);
             const uint32_t slab_step = (uint32_t)slab_bytes >> 4;
             int ia = 0, gi = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+            for (int li = 0; li < n_mine; ++li, ++lt) {
                 const int buf = lt & 1;
+                bool skip;                                 // second half of a 128-row tile: keep the barrier protocol, issue nothing
+                {
+                    long m0l, m_end; int img, ji; bool half;
+                    tile_at(li, ji, m0l, m_end, img, half);
+                    skip = half && hf == 1;
+                }
                 if (lt >= 2) { PROF_T0(); mbar_wait(&acc_empty[buf], ((lt >> 1) - 1) & 1); PROF_ADD(w2); }
                 tc_fence_after_sync();
                 const uint32_t acc = tmem_base + buf * 2 * N + hf * N;
                 uint32_t accumulate = 0;
-                int tap = 0, dx = 0, sa = ia % kSlabStages;
+                int tap = 0, dx = 0, sa = ia % kSlabStages, as = 0, cur_taps = as_taps[0];
                 uint32_t slab_lo = slab_lo0 + sa * slab_step, tap_lo = tap0_lo;
                 for (int g = 0; g < groups; ++g, ++gi) {
                     const int sw = gi % kWStages;
@@ -189,14 +227,17 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                         if (tap == 0) { PROF_T0(); mbar_wait(&a_full[sa], (ia / kSlabStages) & 1); PROF_ADD(w0); }
                         tc_fence_after_sync();
                         const uint32_t a_lo = slab_lo + tap_lo;
-                        umma_f16(acc, umma_desc(a_lo, hi), umma_desc(b_lo, hi), idesc, accumulate);
-                        umma_f16(acc, umma_desc(a_lo + 2, hi), umma_desc(b_lo + 2, hi), idesc, 1u);
-                        umma_f16(acc, umma_desc(a_lo + 4, hi), umma_desc(b_lo + 4, hi), idesc, 1u);
-                        umma_f16(acc, umma_desc(a_lo + 6, hi), umma_desc(b_lo + 6, hi), idesc, 1u);
+                        if (!skip) {
+                            umma_f16(acc, umma_desc(a_lo, hi), umma_desc(b_lo, hi), idesc, accumulate);
+                            umma_f16(acc, umma_desc(a_lo + 2, hi), umma_desc(b_lo + 2, hi), idesc, 1u);
+                            umma_f16(acc, umma_desc(a_lo + 4, hi), umma_desc(b_lo + 4, hi), idesc, 1u);
+                            umma_f16(acc, umma_desc(a_lo + 6, hi), umma_desc(b_lo + 6, hi), idesc, 1u);
+                        }
                         accumulate = 1u;
-                        if (++tap == n_taps) {             // slab fully consumed
+                        if (++tap == cur_taps) {           // slab fully consumed
                             umma_commit(&a_empty[sa]);
                             tap = 0; dx = 0; tap_lo = tap0_lo; ++ia;
+                            cur_taps = as_taps[++as < a_steps ? as : 0];
                             sa = ia % kSlabStages;
                             slab_lo = slab_lo0 + sa * slab_step;
                         } else if (++dx == 3) {
@@ -218,16 +259,16 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
         // ------------------------------------------------------------ epilogue (warps 0..7)
         const int hf = warp >> 2, q = warp & 3;
         int lt = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++lt) {
+        for (int li = 0; li < n_mine; ++li, ++lt) {
             const int buf = lt & 1;
-            const GemmJobDev& job = p.jobs[tile / tiles_per_job];
-            long m0l, m_end; int img_t;
-            tile_rows(tile, m0l, m_end, img_t);
+            long m0l, m_end; int img_t, ji; bool half;
+            tile_at(li, ji, m0l, m_end, img_t, half);
+            const GemmJobDev& job = p.jobs[ji];
             const long m = m0l + hf * 128 + q * 32 + lane;
             // per-tile channel vectors (the job can change from tile to tile)
             {
                 const int t = threadIdx.x;                // 0..255
-                if (t < N) bias_s[buf][t] = job.bias ? job.bias[t] : 0.f;
+                if (t < N) bias_s[buf][t] = (job.bias ? job.bias[t] : 0.f) + (job.bias_img ? job.bias_img[img_t * N + t] : 0.f);
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const int img = (int)(m / p.g.R);
@@ -249,7 +290,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             const bool ln = job.ln_gamma != nullptr;
             float mu = 0.f, rstd = 1.f;
             if (ln) epi_ln_stats<N>(trow, bias_s[buf], job.ln_eps, mu, rstd);
-            if (p.bo_mode & 8) {                           // experiment: no TMEM reads at all
+            if ((p.bo_mode & 8) || (half && hf == 1)) {    // nothing to store (experiment switch / unused half of a 128-row tile)
                 tc_fence_before_sync();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 continue;
@@ -291,7 +332,7 @@ int launch_slab_n(const GemmParams& p, cudaStream_t st) {
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    const int total = p.tiles_per_job * p.n_jobs;
+    const int total = p.n_full + p.n_half;
     const int grid = total < sm_count() ? total : sm_count();
     kern<<<grid, kThreadsSlab, smem, st>>>(p);
     BMC_CUDA(cudaGetLastError());
@@ -313,9 +354,23 @@ int launch_conv_slab(GemmParams p, cudaStream_t st) {
     p.slab_lead = p.n_taps == 9 ? p.g.Wp + 1 : 0;
     p.slab_boxes = (kBM + 2 * p.slab_lead + kBoxRows - 1) / kBoxRows;
     p.per_image = 0;
-    for (int j = 0; j < p.n_jobs; ++j) p.per_image |= p.jobs[j].w_img_stride != 0;   // per-image weights: per-image tiles
-    p.tiles_per_img256 = (p.g.R + kBM - 1) / kBM;
-    p.tiles_per_job = p.per_image ? p.g.B * p.tiles_per_img256 : (int)((p.g.rows() + kBM - 1) / kBM);
+    for (int j = 0; j < p.n_jobs; ++j) {
+        p.per_image |= p.jobs[j].w_img_stride != 0;                                   // per-image weights: per-image tiles
+        for (int sg = 0; sg < p.n_seg; ++sg) p.per_image |= ((p.tap1_mask >> sg) & 1) && p.jobs[j].t1_img_stride[sg] != 0;
+    }
+    if (p.tap1_mask && (p.n != 128 || p.n_taps != 9 || (p.tap1_mask & 1))) {
+        set_error("conv_slab: centre-tap segments need a 3x3, N=128 launch whose first segment is a full 3x3");
+        return BMC_ERR_ARG;
+    }
+    if (p.per_image) {
+        p.full_per_img = p.g.R / kBM;                                                  // R is a multiple of 128
+        p.n_full = p.n_jobs * p.g.B * p.full_per_img;
+        p.n_half = (p.g.R % kBM) ? p.n_jobs * p.g.B : 0;
+    } else {
+        p.full_per_img = 0;
+        p.n_full = p.n_jobs * (int)((p.g.rows() + kBM - 1) / kBM);
+        p.n_half = 0;
+    }
     static int bo = -1;
     // 0 (default, verified on B200): the hardware swizzles on absolute shared-memory address bits,
     // so a row-shifted start needs no base offset; 1 sets the descriptor's base-offset field

@@ -130,13 +130,18 @@ struct JobSpec {
     bool out_f32 = false;    // conv_o: fp32 [rows][32] side buffer
     int hid32 = -1;          // hidden-state convs: also keep an fp32 copy [rows][128] (forward() output)
     int ln = -1;
+    // centre-tap-only segments appended after `segs` (slab kernel only, gemm.cuh GemmJobDev::t1_*):
+    int mix_slot = -1, mix_pair = -1;   // + M_pair[b] . x  with x in arena slot mix_slot (fused BIE, bie_fused.cu)
+    int ident_slot = -1;                // + I . x : a residual add done by the tensor core
 };
 
 struct Op {
-    enum Kind { kGemm, kAtt, kSoftmax } kind;
+    enum Kind { kGemm, kAtt, kSoftmax, kBieFront, kFold } kind;
     GemmParams gp;
     AttParams ap;
     SoftmaxParams sp;
+    BieFrontParams fp;
+    FoldParams dp;
 };
 
 }  // namespace
@@ -146,7 +151,7 @@ struct bmc_model {
     std::vector<WeightSpec> weights;
     std::vector<LnSpec> lns;
     std::map<std::string, int> widx;
-    int w_rows_total = 0;
+    int w_rows_total = 0, ident_row = 0;
     size_t f32_floats = 0, kmap_ints = 0;
     // device weights
     act_t* w_dev = nullptr;
@@ -158,7 +163,9 @@ struct bmc_model {
     Geom g;
     int n_slots = 0, n_split = 1, pix_per_split = 0;
     size_t ws_bytes = 0;
-    size_t off_mi = 0, off_a32 = 0, off_p = 0, off_partial = 0, off_hid32 = 0;
+    size_t off_mi = 0, off_a32 = 0, off_p = 0, off_partial = 0, off_hid32 = 0, off_bimg = 0, off_gpart = 0, off_spart = 0;
+    bool fused = true;                     // product plan: fused BIE 1x1 / attention section (bie_fused.cu)
+    bool allow_fused = true;
     char* ws = nullptr;
     CUtensorMap map_act, map_att, map_mi, map_mi64, map_w128, map_w32, map_p;
     // plan
@@ -182,6 +189,9 @@ struct bmc_model {
     act_t* p_ptr() const { return reinterpret_cast<act_t*>(ws + off_p); }
     float* partial_ptr() const { return reinterpret_cast<float*>(ws + off_partial); }
     float* hid32_ptr(int i) const { return reinterpret_cast<float*>(ws + off_hid32) + (size_t)i * g.rows() * 128; }
+    float* bimg_ptr() const { return reinterpret_cast<float*>(ws + off_bimg); }
+    float* gpart_ptr() const { return reinterpret_cast<float*>(ws + off_gpart); }
+    float* spart_ptr() const { return reinterpret_cast<float*>(ws + off_spart); }
 };
 
 namespace {
@@ -265,6 +275,9 @@ void register_weights(bmc_model* m) {
             add_weight(m, n, std::string("neuro.") + n, 128, 128, 9, {seg_range(0, 128, 128)});
         add_weight(m, "o", "neuro.conv_o", 256, 32, 9, {seg_range(0, 128, 128), seg_range(128, 128, 128)});
     }
+    // 128x128 identity in the weight layout [2][128][64]: residual adds as one more K segment (gemm.cuh t1_*)
+    m->ident_row = m->w_rows_total;
+    m->w_rows_total += 256;
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -292,16 +305,31 @@ struct Builder {
         p.maps[4] = m->map_att;                 // act arena, 64-row boxes (slab kernel)
         p.maps[5] = m->map_mi64;
         p.n_jobs = (int)jobs.size();
-        p.n_seg = (int)jobs[0].segs.size();
+        const int n_plain = (int)jobs[0].segs.size();
+        p.n_seg = n_plain + (jobs[0].mix_slot >= 0) + (jobs[0].ident_slot >= 0);
         p.n_taps = taps;
         for (int t = 0; t < taps; ++t) p.tap_off[t] = taps == 9 ? (t / 3 - 1) * g.Wp + (t % 3 - 1) : 0;
         p.n = n; p.g = g; p.tiles_per_img = g.R / kTileM;
-        for (int s = 0; s < p.n_seg; ++s) p.chunks[s] = jobs[0].segs[s].kind == 1 ? 1 : 2;
+        for (int s = 0; s < p.n_seg; ++s) p.chunks[s] = (s < n_plain && jobs[0].segs[s].kind == 1) ? 1 : 2;
         for (int j = 0; j < p.n_jobs; ++j) {
             const JobSpec& js = jobs[j];
             GemmJobDev& d = p.jobs[j];
+            std::vector<Src> segs = js.segs;
+            if (js.mix_slot >= 0) {
+                const int sg = (int)segs.size();
+                segs.push_back({0, js.mix_slot});
+                p.tap1_mask |= 1 << sg;
+                d.t1_map[sg] = 3; d.t1_row[sg] = js.mix_pair * g.B * 256; d.t1_img_stride[sg] = 256;
+                d.bias_img = m->bimg_ptr() + (size_t)js.mix_pair * g.B * 128;
+            }
+            if (js.ident_slot >= 0) {
+                const int sg = (int)segs.size();
+                segs.push_back({0, js.ident_slot});
+                p.tap1_mask |= 1 << sg;
+                d.t1_map[sg] = 2; d.t1_row[sg] = m->ident_row; d.t1_img_stride[sg] = 0;
+            }
             for (int s = 0; s < p.n_seg; ++s) {
-                const Src& src = js.segs[s];
+                const Src& src = segs[s];
                 if (src.kind == 1) {
                     d.a_map[s] = 1; d.a_map64[s] = 5; d.a_row_base[s] = 0; d.a_ptr[s] = m->mi_ptr(); d.a_ld[s] = 64; d.a_rows[s] = g.rows();
                 } else {
@@ -363,6 +391,7 @@ struct Builder {
     // BIE.forward (submodules.py:58-77) for 1 or 2 independent instances sharing the weights.
     // Consumes (releases) its input slots.
     std::vector<Tri> bie(const std::string& p, const std::vector<Tri>& in) {
+        if (m->fused) return bie_fused(p, in);
         const int I = (int)in.size();
         std::vector<std::array<int, 2>> t(I), r(I), y(I), c(I), v(I), nx(I);
         std::vector<int> ns(I);
@@ -431,6 +460,81 @@ struct Builder {
         return out;
     }
 
+    // BIE.forward with the 1x1 / attention section fused (bie_fused.cu): conv1 of the two
+    // ResidualBlocks, bie_front_tc (x_s' and the attention partial sums), att_fold (per-image mix
+    // matrices), then conv2 of the ResidualBlocks with the mix segment:
+    //   x_k' = out_k + x_{1-k}_ = M_k[b] x_k + P_k bv_k + x_{1-k} + conv2(relu(conv1(x_{1-k})))
+    std::vector<Tri> bie_fused(const std::string& p, const std::vector<Tri>& in) {
+        const int I = (int)in.size();
+        std::vector<std::array<int, 2>> t(I), nx(I);
+        std::vector<int> ns(I);
+        std::vector<JobSpec> jobs;
+        auto xk = [&](int i, int k) { return k == 0 ? in[i].x1 : in[i].x2; };
+        const char* resn[2] = {".conv1", ".conv2"};
+        for (int i = 0; i < I; ++i) for (int k = 0; k < 2; ++k) {
+            t[i][k] = alloc();
+            JobSpec j; j.segs = {{0, xk(i, k)}}; j.weight = W(p + resn[k] + ".conv1"); j.relu = true; j.out_slot = t[i][k];
+            jobs.push_back(j);
+        }
+        gemm(jobs, 128, 9); jobs.clear();
+        for (int i = 0; i < I; ++i) ns[i] = alloc();
+        if (!m->dry) {
+            const Geom& g = m->g;
+            Op f;
+            f.kind = Op::kBieFront;
+            memset(&f.fp, 0, sizeof(f.fp));
+            BieFrontParams& q = f.fp;
+            q.map_act = m->map_act; q.map_w = m->map_w128;
+            q.n_inst = I;
+            for (int i = 0; i < I; ++i) {
+                q.inst[i].x1_row = (int)(in[i].x1 * g.rows()); q.inst[i].x2_row = (int)(in[i].x2 * g.rows());
+                q.inst[i].xs_row = (int)(in[i].xs * g.rows()); q.inst[i].out_row = (int)(ns[i] * g.rows());
+            }
+            const WeightSpec &wf = m->weights[W(p + ".convf1")], &wc = m->weights[W(p + ".clustering")],
+                             &wu = m->weights[W(p + ".unclustering")];
+            q.wf_row = wf.row_base; q.wc_row = wc.row_base; q.wu_row = wu.row_base;
+            q.bf = m->f32_dev + wf.bias_off; q.bc = m->f32_dev + wc.bias_off; q.bu = m->f32_dev + wu.bias_off;
+            const LnSpec& ln = m->lns[W(p + ".norm_s")];
+            q.ln_gamma = m->f32_dev + ln.gamma_off; q.ln_beta = m->f32_dev + ln.beta_off; q.ln_eps = 1e-6f;
+            q.act_base = m->slot_ptr(0); q.out_base = m->slot_ptr(0);
+            q.g_partial = m->gpart_ptr(); q.s_partial = m->spart_ptr();
+            q.g = g; q.tiles_per_img = g.R / 128;
+            q.total_tiles = I * g.B * q.tiles_per_img;
+            const int grid = bie_front_grid(q.total_tiles);
+            q.tiles_per_cta = (q.total_tiles + grid - 1) / grid;
+            q.lcm = bie_front_lcm(q.tiles_per_cta, q.tiles_per_img);
+            m->ops.push_back(f);
+            Op d;
+            d.kind = Op::kFold;
+            memset(&d.dp, 0, sizeof(d.dp));
+            FoldParams& fo = d.dp;
+            fo.g_partial = q.g_partial; fo.s_partial = q.s_partial;
+            fo.n_inst = I; fo.B = g.B; fo.tiles_per_img = q.tiles_per_img; fo.tiles_per_cta = q.tiles_per_cta;
+            fo.total_tiles = q.total_tiles; fo.lcm = q.lcm;
+            fo.w_base = m->w_dev;
+            const WeightSpec &wv1 = m->weights[W(p + ".v1")], &wv2 = m->weights[W(p + ".v2")];
+            fo.wv_row[0] = wv1.row_base; fo.wv_row[1] = wv2.row_base;
+            fo.bv[0] = m->f32_dev + wv1.bias_off; fo.bv[1] = m->f32_dev + wv2.bias_off;
+            fo.scale = 1.0f / sqrtf(128.f);                              // nf ** -0.5, submodules.py:47
+            fo.m_base = m->p_ptr(); fo.bias_img = m->bimg_ptr();
+            m->ops.push_back(d);
+        }
+        for (int i = 0; i < I; ++i) for (int k = 0; k < 2; ++k) {
+            nx[i][k] = alloc();
+            JobSpec j; j.segs = {{0, t[i][1 - k]}}; j.weight = W(p + resn[1 - k] + ".conv2");
+            j.mix_slot = xk(i, k); j.mix_pair = i * 2 + k; j.ident_slot = xk(i, 1 - k); j.out_slot = nx[i][k];
+            jobs.push_back(j);
+        }
+        gemm(jobs, 128, 9); jobs.clear();
+        std::vector<Tri> out(I);
+        for (int i = 0; i < I; ++i) {
+            for (int k = 0; k < 2; ++k) release(t[i][k]);
+            release(in[i].x1); release(in[i].x2); release(in[i].xs);
+            out[i] = {nx[i][0], nx[i][1], ns[i]};
+        }
+        return out;
+    }
+
     void build_plain() {
         const std::string blk = "neuro.para_reschunk.";
         const int H = m->slot_h[0];
@@ -489,7 +593,8 @@ struct Builder {
             jobs.assign(4, JobSpec());
             for (int j = 0; j < 4; ++j) {
                 xo[j] = alloc();
-                jobs[j].segs = {{0, t[j]}}; jobs[j].weight = W(p + nm[j] + ".conv2"); jobs[j].res_slot = xin[j]; jobs[j].out_slot = xo[j];
+                jobs[j].segs = {{0, t[j]}}; jobs[j].weight = W(p + nm[j] + ".conv2"); jobs[j].out_slot = xo[j];
+                if (m->fused) jobs[j].ident_slot = xin[j]; else jobs[j].res_slot = xin[j];
             }
             gemm(jobs, 128, 9);
             for (int j = 0; j < 4; ++j) { release(t[j]); release(xin[j]); }
@@ -527,11 +632,59 @@ void drop_graph(bmc_model* m) {
     m->eager_runs = 0;
 }
 
+int launch_op(bmc_model* m, const Op& op, cudaStream_t st);
+
+// BMC_OP_TIMES=1: time every launch of the plan with CUDA events (warm caches, back to back) and print the
+// list -- the in-context complement of an ncu launch list, whose replays start from a flushed L2.
+int time_ops(bmc_model* m, cudaStream_t st) {
+    const char* names[] = {"conv_gemm", "att", "att_softmax", "bie_front", "att_fold"};
+    std::vector<cudaEvent_t> ev(m->ops.size() + 1);
+    for (auto& e : ev) cudaEventCreate(&e);
+    for (int rep = 0; rep < 3; ++rep) {
+        cudaEventRecord(ev[0], st);
+        for (size_t i = 0; i < m->ops.size(); ++i) {
+            int rc = launch_op(m, m->ops[i], st);
+            if (rc) return rc;
+            cudaEventRecord(ev[i + 1], st);
+        }
+    }
+    BMC_CUDA(cudaStreamSynchronize(st));
+    float total = 0.f;
+    for (size_t i = 0; i < m->ops.size(); ++i) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+        const Op& op = m->ops[i];
+        if (op.kind == Op::kGemm)
+            printf("optime %3zu %-12s jobs %d segs %d taps %d n %3d mix %d res %d : %8.1f us\n", i, names[op.kind], op.gp.n_jobs,
+                   op.gp.n_seg, op.gp.n_taps, op.gp.n, op.gp.tap1_mask, op.gp.jobs[0].residual != nullptr, ms * 1e3f);
+        else
+            printf("optime %3zu %-12s : %8.1f us\n", i, names[op.kind], ms * 1e3f);
+        total += ms;
+    }
+    printf("optime total %.1f us over %zu launches\n", total * 1e3f, m->ops.size());
+    for (auto& e : ev) cudaEventDestroy(e);
+    return BMC_OK;
+}
+
+int launch_op(bmc_model* m, const Op& op, cudaStream_t st) {
+    if (op.kind == Op::kGemm) return launch_conv_gemm(op.gp, m->simt, st);
+    if (op.kind == Op::kAtt) return launch_att(op.ap, m->simt, st);
+    if (op.kind == Op::kBieFront) return launch_bie_front(op.fp, st);
+    if (op.kind == Op::kFold) return launch_att_fold(op.dp, st);
+    return launch_att_softmax(op.sp, st);
+}
+
 int run_ops(bmc_model* m, cudaStream_t st) {
+    static int want_times = -1;
+    if (want_times < 0) { const char* e = getenv("BMC_OP_TIMES"); want_times = e ? atoi(e) : 0; }
+    static int calls = 0;
+    if (want_times && ++calls == 4) { want_times = 0; return time_ops(m, st); }
     for (const Op& op : m->ops) {
         int rc = BMC_OK;
         if (op.kind == Op::kGemm) rc = launch_conv_gemm(op.gp, m->simt, st);
         else if (op.kind == Op::kAtt) rc = launch_att(op.ap, m->simt, st);
+        else if (op.kind == Op::kBieFront) rc = launch_bie_front(op.fp, st);
+        else if (op.kind == Op::kFold) rc = launch_att_fold(op.dp, st);
         else rc = launch_att_softmax(op.sp, st);
         if (rc) return rc;
     }
@@ -649,6 +802,10 @@ extern "C" BMC_EXPORT int bmc_model_load_state_dict(bmc_model_t* m, const char* 
         if (rc) return rc;
         BMC_CUDA(cudaMemcpyAsync(m->f32_dev + w.bias_off, bs, w.n_out * 4, cudaMemcpyDeviceToDevice, st));
     }
+    {
+        int rc = launch_fill_identity(m->w_dev + (size_t)m->ident_row * 64, st);
+        if (rc) return rc;
+    }
     for (auto& ln : m->lns) {
         const float *g = nullptr, *b = nullptr;
         int rc = find(ln.prefix + ".weight", 128, &g);
@@ -680,9 +837,24 @@ extern "C" BMC_EXPORT int bmc_model_configure(bmc_model_t* m, int batch, int H, 
     drop_graph(m);
     m->bound = false;
     m->dry = true;
+    // the fused BIE plan needs the slab kernel (mix segment); very wide images fall back to the unfused plan
+    {
+        GemmParams probe;
+        memset(&probe, 0, sizeof(probe));
+        probe.n = 128; probe.n_taps = 9; probe.g = m->g;
+        const char* e = getenv("BMC_FUSED");
+        m->allow_fused = slab_supported(probe) && !(e && !atoi(e));
+    }
     Builder b{m};
+    m->fused = false;
     b.build();
     m->n_slots = m->slots_hi;
+    if (m->allow_fused) {                 // arena must hold either plan (the SIMT cross-check runs the unfused one)
+        m->fused = true;
+        b.build();
+        m->n_slots = std::max(m->n_slots, m->slots_hi);
+    }
+    m->fused = m->allow_fused && !m->simt;
     const int chunks = m->g.R / 64;
     int want = (sm_count() + 4 * batch - 1) / (4 * batch);
     want = std::max(1, std::min(want, chunks));
@@ -695,6 +867,13 @@ extern "C" BMC_EXPORT int bmc_model_configure(bmc_model_t* m, int batch, int H, 
     m->off_p = off; off += align_up((size_t)kMaxPairs * batch * 256 * 128, 1024);
     m->off_partial = off; off += align_up((size_t)kMaxPairs * batch * m->n_split * 128 * 128 * 4, 1024);
     m->off_hid32 = off; off += align_up((size_t)(m->kind == BMC_MODEL_BMCNET ? 3 : 1) * rows * 512, 1024);
+    m->off_bimg = off; off += align_up((size_t)kMaxPairs * batch * 128 * 4, 1024);
+    {
+        const int n_inst = m->kind == BMC_MODEL_BMCNET ? 2 : 1;
+        const int slots = bie_front_slots(n_inst * batch * (m->g.R / 128), m->g.R / 128);
+        m->off_gpart = off; off += align_up((size_t)slots * 2 * 128 * 128 * 4, 1024);
+        m->off_spart = off; off += align_up((size_t)slots * 2 * 128 * 4, 1024);
+    }
     m->ws_bytes = off;
     m->configured = true;
     return BMC_OK;
@@ -733,6 +912,16 @@ extern "C" BMC_EXPORT int bmc_model_launches_per_step(const bmc_model_t* m) { re
 extern "C" BMC_EXPORT int bmc_model_set_debug_simt(bmc_model_t* m, int enable) {
     BMC_REQUIRE(m, "set_debug_simt: NULL model");
     m->simt = enable ? 1 : 0;
+    const bool fused = m->allow_fused && !m->simt;
+    if (fused != m->fused) {              // the SIMT cross-check runs the unfused dataflow: rebuild the plan
+        m->fused = fused;
+        if (m->bound) {
+            drop_graph(m);
+            m->dry = false;
+            Builder b{m};
+            b.build();
+        }
+    }
     return BMC_OK;
 }
 

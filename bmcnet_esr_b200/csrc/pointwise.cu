@@ -218,7 +218,20 @@ __global__ void repack_weight(const float* __restrict__ src, const int* __restri
     dst[((long)(k >> 6) * w_rows + w_row_base + n) * 64 + (k & 63)] = to_act(v);
 }
 
+__global__ void fill_identity(act_t* __restrict__ dst) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // [2][128][64]
+    if (idx >= 2 * 128 * 64) return;
+    const int kc = idx >> 13, n = (idx >> 6) & 127, kk = idx & 63;
+    dst[idx] = to_act(kc * 64 + kk == n ? 1.f : 0.f);
+}
+
 }  // namespace
+
+int launch_fill_identity(act_t* dst, cudaStream_t st) {
+    fill_identity<<<64, 256, 0, st>>>(dst);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
 
 int launch_layernorm(const act_t* in, const float* gamma, const float* beta, float eps, long rows,
                      act_t* out, cudaStream_t st) {
