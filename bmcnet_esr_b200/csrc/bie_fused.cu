@@ -123,8 +123,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     const int B = p.g.B, R = p.g.R;
 
     if (warp == 0) {
-        // ------------------------------------------------------------ input tiles
-        if (lane == 0) {
+        // ------------------------------------------------------------ input tiles (lane l issues box l of the six)
+        {
             int lt = 0;
             for (int T = T0; T < T1; ++T, ++lt) {
                 const int img = T / tpi, t = T - img * tpi;
@@ -132,37 +132,35 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 const int row0 = b * R + t * kTile;
                 if (lt > 0) mbar_wait(&in_empty, (lt - 1) & 1);
                 const BieInst& in = p.inst[inst];
-                mbar_expect_tx(&in_full, 3 * kTensBytes);
-                tma_load_2d(s_xs, &p.map_act, &in_full, 0, in.xs_row + row0);
-                tma_load_2d(s_xs + kHalfBytes, &p.map_act, &in_full, 64, in.xs_row + row0);
-                tma_load_2d(s_x1, &p.map_act, &in_full, 0, in.x1_row + row0);
-                tma_load_2d(s_x1 + kHalfBytes, &p.map_act, &in_full, 64, in.x1_row + row0);
-                tma_load_2d(s_x2, &p.map_act, &in_full, 0, in.x2_row + row0);
-                tma_load_2d(s_x2 + kHalfBytes, &p.map_act, &in_full, 64, in.x2_row + row0);
-                if (T + 1 < T1) {                  // start the HBM read of the next tile now; its smem buffers free up a tile later
+                if (lane == 0) mbar_expect_tx(&in_full, 3 * kTensBytes);
+                __syncwarp();
+                if (lane < 6) {
+                    const int which = lane >> 1;                       // 0: x_s, 1: x_1, 2: x_2
+                    const int trow = which == 0 ? in.xs_row : (which == 1 ? in.x1_row : in.x2_row);
+                    tma_load_2d(smem + which * kTensBytes + (lane & 1) * kHalfBytes, &p.map_act, &in_full, (lane & 1) * 64, trow + row0);
+                } else if (lane < 12 && T + 1 < T1) {
+                    // start the HBM read of the next tile now; its smem buffers free up a tile later
                     const int img2 = (T + 1) / tpi, t2 = (T + 1) - img2 * tpi;
                     const int inst2 = img2 / B, b2 = img2 - inst2 * B;
-                    const int row2 = b2 * R + t2 * kTile;
                     const BieInst& in2 = p.inst[inst2];
-                    for (int c0 = 0; c0 < 128; c0 += 64) {
-                        tma_prefetch_l2_2d(&p.map_act, c0, in2.xs_row + row2);
-                        tma_prefetch_l2_2d(&p.map_act, c0, in2.x1_row + row2);
-                        tma_prefetch_l2_2d(&p.map_act, c0, in2.x2_row + row2);
-                    }
+                    const int which = (lane - 6) >> 1;
+                    const int trow = which == 0 ? in2.xs_row : (which == 1 ? in2.x1_row : in2.x2_row);
+                    tma_prefetch_l2_2d(&p.map_act, (lane & 1) * 64, trow + b2 * R + t2 * kTile);
                 }
             }
         }
     } else if (warp == 1) {
         // ------------------------------------------------------------ weight ring: Wf[0..3], Wc[0..1], Wu[0..3] per tile
-        if (lane == 0) {
-            int wi = 0;
+        // lanes 0..4 each own one ring stage and issue its loads (two chunks per tile each)
+        if (lane < kFrontWStages) {
+            int round = 0;                                             // uses of this lane's stage so far
             for (int T = T0; T < T1; ++T) {
-                for (int j = 0; j < kWChunksPerTile; ++j, ++wi) {
-                    const int st = wi % kFrontWStages;
-                    if (wi >= kFrontWStages) mbar_wait(&w_empty[st], ((wi / kFrontWStages) - 1) & 1);
+                for (int h = 0; h < kWChunksPerTile / kFrontWStages; ++h, ++round) {
+                    const int j = h * kFrontWStages + lane;            // chunk of the tile; (tile*10 + j) % 5 == lane
+                    if (round > 0) mbar_wait(&w_empty[lane], (round - 1) & 1);
                     const int row = j < 4 ? p.wf_row + j * 128 : (j < 6 ? p.wc_row + (j - 4) * 128 : p.wu_row + (j - 6) * 128);
-                    mbar_expect_tx(&w_full[st], kHalfBytes);
-                    tma_load_2d(s_w + st * kHalfBytes, &p.map_w, &w_full[st], 0, row);
+                    mbar_expect_tx(&w_full[lane], kHalfBytes);
+                    tma_load_2d(s_w + lane * kHalfBytes, &p.map_w, &w_full[lane], 0, row);
                 }
             }
         }

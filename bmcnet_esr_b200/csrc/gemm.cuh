@@ -67,6 +67,7 @@ struct alignas(64) GemmParams {
     int tap_off[9];            // row shift of each tap: dy*Wp + dx
     int n;                     // output channels: 128 or 32
     int tap1_mask;             // bit s: segment s contributes its centre tap only, with weights from GemmJobDev::t1_*
+    int pimg_mask;             // subset of tap1_mask whose weights are per image (filled in by the slab launcher)
     Geom g;
     int tiles_per_img;         // R / 128
     // slab kernel (gemm_slab.cu); filled in by its launcher

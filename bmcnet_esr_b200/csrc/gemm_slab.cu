@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
     __shared__ uint64_t a_full[kSlabStages], a_empty[kSlabStages], w_full[kWStages], w_empty[kWStages];
     __shared__ uint64_t acc_full[2], acc_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float bias_s[2][N];
+    __shared__ __align__(16) float bias_s[2][N];           // [128-row half][channel], rewritten per tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long rows_total = p.g.rows();
@@ -59,7 +59,9 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
     int a_steps = 0;
     int as_seg[kMaxASteps], as_chunk[kMaxASteps], as_k0[kMaxASteps], as_cs[kMaxASteps], as_taps[kMaxASteps];
     const int tap1_mask = p.tap1_mask;                  // centre-tap-only segments (per-image mix matrix / identity)
+    const int pimg_mask = p.pimg_mask;                  // ... of which: weights differ per image
     int steps = 0;                                      // K steps (one tap of one chunk) per tile
+    uint32_t t1_as = 0, pm_as = 0;                      // per (segment, chunk) step: centre-tap only / per-image weights
     {
         int seg_chunk0 = 0;
         for (int s = 0; s < p.n_seg; ++s) {
@@ -67,6 +69,8 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             for (int c = 0; c < p.chunks[s]; ++c, ++a_steps) {
                 as_seg[a_steps] = s; as_chunk[a_steps] = c; as_k0[a_steps] = seg_chunk0 + c; as_cs[a_steps] = p.chunks[s];
                 as_taps[a_steps] = taps_s;
+                if (taps_s == 1 && n_taps != 1) t1_as |= 1u << a_steps;
+                if ((pimg_mask >> s) & 1) pm_as |= 1u << a_steps;
                 steps += taps_s;
             }
             if (!((tap1_mask >> s) & 1)) seg_chunk0 += n_taps * p.chunks[s];
@@ -105,7 +109,6 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             m_end = (long)(img + 1) * p.g.R;
         }
     };
-    const int groups = (steps + kWGroup - 1) / kWGroup; // weight stages per tile
 
     if (threadIdx.x == 0) {
         // "empty" / "acc_full" barriers collect one tcgen05.commit from each of the two MMA issuers
@@ -122,7 +125,9 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
 
     if (warp == 8) {
         // ------------------------------------------------------------ activation slabs
-        if (lane == 0) {
+        // The whole warp walks the loop; lane b issues box b, so the boxes of a slab leave in one
+        // instruction instead of a serial loop (a single issuing thread was the supply bottleneck).
+        {
             int it = 0;
             for (int li = 0; li < n_mine; ++li) {
                 long m0l, m_end; int img, ji; bool half;
@@ -134,22 +139,27 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     const int st = it % kSlabStages;
                     if (it >= kSlabStages) { PROF_T0(); mbar_wait(&a_empty[st], ((it / kSlabStages) - 1) & 1); PROF_ADD(w0); }
                     uint8_t* dst = smem + st * slab_bytes;
-                    if ((p.bo_mode & 1) && it >= kSlabStages) { mbar_arrive(&a_full[st]); continue; }   // experiment: no TMA
+                    if ((p.bo_mode & 1) && it >= kSlabStages) { if (lane == 0) mbar_arrive(&a_full[st]); continue; }   // experiment: no TMA
                     const CUtensorMap* map = &p.maps[job.a_map64[s]];
                     const bool mix = (tap1_mask >> s) & 1;   // centre tap only: just the tile's own 256 rows
                     const int row0 = job.a_row_base[s] + m0 - (mix ? 0 : p.slab_lead);
                     const int boxes = mix ? kBM / kBoxRows : p.slab_boxes;
-                    mbar_expect_tx(&a_full[st], boxes * kBoxBytes);
-                    for (int b = 0; b < boxes; ++b)
-                        tma_load_2d(dst + b * kBoxBytes, map, &a_full[st], job.a_col_base[s] + as_chunk[as] * kChunkK,
-                                    row0 + b * kBoxRows);
+                    if (lane == 0) mbar_expect_tx(&a_full[st], boxes * kBoxBytes);
+                    __syncwarp();
+                    if (lane < boxes)
+                        tma_load_2d(dst + lane * kBoxBytes, map, &a_full[st], job.a_col_base[s] + as_chunk[as] * kChunkK,
+                                    row0 + lane * kBoxRows);
                 }
             }
-            if (prof_on) { p.prof[blockIdx.x * 16 + 0] = w0; p.prof[blockIdx.x * 16 + 1] = clock64() - t_begin; }
+            if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 0] = w0; p.prof[blockIdx.x * 16 + 1] = clock64() - t_begin; }
         }
     } else if (warp == 9) {
-        // ------------------------------------------------------------ weight tiles, kWGroup taps per stage
-        if (lane == 0) {
+        // ------------------------------------------------------------ weight tiles
+        // A stage holds the weight tiles of two consecutive K steps; a step whose weights are per image
+        // (the mix matrix) takes a stage alone, with one copy per 128-row half of the tile, because the
+        // two halves of a tile can belong to different images (image pitch R is a multiple of 128, not 256).
+        // The whole warp walks the loop; lane j issues the TMA of entry j of the stage.
+        {
             int gi = 0;
             for (int li = 0; li < n_mine; ++li) {
                 long m0l, m_end; int img, ji; bool half;
@@ -157,32 +167,44 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                 const GemmJobDev& job = p.jobs[ji];
                 const CUtensorMap* map = &p.maps[job.w_map];
                 const int w_row0 = job.w_row_base + img * job.w_img_stride;
+                const int img_h0 = min((int)(m0l / p.g.R), p.g.B - 1), img_h1 = min((int)((m0l + 128) / p.g.R), p.g.B - 1);
                 int as = 0, tap = 0;
-                for (int g = 0; g < groups; ++g, ++gi) {
+                while (as < a_steps) {
                     const int st = gi % kWStages;
                     if (gi >= kWStages) { PROF_T0(); mbar_wait(&w_empty[st], ((gi / kWStages) - 1) & 1); PROF_ADD(w0); }
-                    const int cnt = min(kWGroup, steps - g * kWGroup);
-                    if ((p.bo_mode & 1) && gi >= kWStages) {                               // experiment: no TMA
-                        mbar_arrive(&w_full[st]);
-                        for (int j = 0; j < cnt; ++j) if (++tap == as_taps[as]) { tap = 0; ++as; }
-                        continue;
-                    }
-                    mbar_expect_tx(&w_full[st], cnt * kWBytes);
-                    for (int j = 0; j < cnt; ++j) {
+                    uint8_t* dst = smem_w + st * kWStageBytes + (lane & 1) * kWBytes;
+                    if ((pm_as >> as) & 1u) {
                         const int sg = as_seg[as];
-                        if ((tap1_mask >> sg) & 1) {                                       // own weights, chunk-major [chunks][128][64]
-                            tma_load_2d(smem_w + st * kWStageBytes + j * kWBytes, &p.maps[job.t1_map[sg]], &w_full[st], 0,
-                                        job.t1_row[sg] + img * job.t1_img_stride[sg] + as_chunk[as] * 128);
-                        } else {
-                            const int kchunk = as_k0[as] + tap * as_cs[as];                // K order (seg, tap, chunk)
-                            tma_load_2d(smem_w + st * kWStageBytes + j * kWBytes, map, &w_full[st], 0,
-                                        kchunk * job.w_rows + w_row0);
+                        if (lane == 0) mbar_expect_tx(&w_full[st], 2 * kWBytes);
+                        __syncwarp();
+                        if (lane < 2)
+                            tma_load_2d(dst, &p.maps[job.t1_map[sg]], &w_full[st], 0,
+                                        job.t1_row[sg] + as_chunk[as] * 128 + (lane ? img_h1 : img_h0) * job.t1_img_stride[sg]);
+                        ++as;                                                              // per-image segments are centre-tap only
+                    } else {
+                        // second entry of the stage: the next step, unless it is a per-image one
+                        int as2 = as, tap2 = tap + 1;
+                        if (tap2 == (((t1_as >> as) & 1u) ? 1 : n_taps)) { tap2 = 0; ++as2; }
+                        const bool two = as2 < a_steps && !((pm_as >> as2) & 1u);
+                        if (lane == 0) mbar_expect_tx(&w_full[st], (two ? 2 : 1) * kWBytes);
+                        __syncwarp();
+                        if (lane < (two ? 2 : 1)) {
+                            const int asl = lane ? as2 : as, tapl = lane ? tap2 : tap;     // this lane's step
+                            if ((t1_as >> asl) & 1u) {                                     // own static weights (identity)
+                                const int sj = as_seg[asl];
+                                tma_load_2d(dst, &p.maps[job.t1_map[sj]], &w_full[st], 0, job.t1_row[sj] + as_chunk[asl] * 128);
+                            } else {
+                                const int kchunk = as_k0[asl] + tapl * as_cs[asl];         // K order (seg, tap, chunk)
+                                tma_load_2d(dst, map, &w_full[st], 0, kchunk * job.w_rows + w_row0);
+                            }
                         }
-                        if (++tap == as_taps[as]) { tap = 0; ++as; }
+                        as = as2; tap = tap2;
+                        if (two) { if (++tap == (((t1_as >> as) & 1u) ? 1 : n_taps)) { tap = 0; ++as; } }
                     }
+                    ++gi;
                 }
             }
-            if (prof_on) { p.prof[blockIdx.x * 16 + 2] = w0; p.prof[blockIdx.x * 16 + 3] = clock64() - t_begin; }
+            if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 2] = w0; p.prof[blockIdx.x * 16 + 3] = clock64() - t_begin; }
         }
     } else if (warp >= 10) {
         // ------------------------------------------------------------ MMA issuers
@@ -216,14 +238,15 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                 tc_fence_after_sync();
                 const uint32_t acc = tmem_base + buf * 2 * N + hf * N;
                 uint32_t accumulate = 0;
-                int tap = 0, dx = 0, sa = ia % kSlabStages, as = 0, cur_taps = as_taps[0];
+                int tap = 0, dx = 0, sa = ia % kSlabStages, as = 0, cur_taps = (t1_as & 1u) ? 1 : n_taps;
                 uint32_t slab_lo = slab_lo0 + sa * slab_step, tap_lo = tap0_lo;
-                for (int g = 0; g < groups; ++g, ++gi) {
+                while (as < a_steps) {
                     const int sw = gi % kWStages;
                     { PROF_T0(); mbar_wait(&w_full[sw], (gi / kWStages) & 1); PROF_ADD(w1); }
-                    const int cnt = min(kWGroup, steps - g * kWGroup);
-                    uint32_t b_lo = w_lo0 + sw * (kWStageBytes >> 4);
-                    for (int j = 0; j < cnt; ++j, b_lo += kWBytes >> 4) {
+                    const uint32_t b_base = w_lo0 + sw * (kWStageBytes >> 4);
+                    const bool pm = (pm_as >> as) & 1u;                 // per-image weights: one copy per half, alone in its stage
+                    for (int e = 0; e < 2; ++e) {
+                        const uint32_t b_lo = b_base + (pm ? hf : e) * (kWBytes >> 4);
                         if (tap == 0) { PROF_T0(); mbar_wait(&a_full[sa], (ia / kSlabStages) & 1); PROF_ADD(w0); }
                         tc_fence_after_sync();
                         const uint32_t a_lo = slab_lo + tap_lo;
@@ -236,8 +259,8 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                         accumulate = 1u;
                         if (++tap == cur_taps) {           // slab fully consumed
                             umma_commit(&a_empty[sa]);
-                            tap = 0; dx = 0; tap_lo = tap0_lo; ++ia;
-                            cur_taps = as_taps[++as < a_steps ? as : 0];
+                            tap = 0; dx = 0; tap_lo = tap0_lo; ++ia; ++as;
+                            cur_taps = ((t1_as >> as) & 1u) ? 1 : n_taps;
                             sa = ia % kSlabStages;
                             slab_lo = slab_lo0 + sa * slab_step;
                         } else if (++dx == 3) {
@@ -245,8 +268,11 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                         } else {
                             tap_lo += 8u;
                         }
+                        // the stage's second entry is the next step, unless this or that one is per-image
+                        if (pm || as >= a_steps || ((pm_as >> as) & 1u)) break;
                     }
                     umma_commit(&w_empty[sw]);
+                    ++gi;
                 }
                 umma_commit(&acc_full[buf]);
             }
@@ -268,7 +294,12 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             // per-tile channel vectors (the job can change from tile to tile)
             {
                 const int t = threadIdx.x;                // 0..255
-                if (t < N) bias_s[buf][t] = (job.bias ? job.bias[t] : 0.f) + (job.bias_img ? job.bias_img[img_t * N + t] : 0.f);
+                asm volatile("bar.sync 1, 256;" ::: "memory");      // every warp is done with the previous tile's vectors
+                if (t < 2 * N) {                           // per half: the two halves of a tile may be different images
+                    const int hb = t / N, n = t - hb * N;
+                    const int img_h = p.per_image ? img_t : min((int)((m0l + hb * 128) / p.g.R), p.g.B - 1);
+                    bias_s[hb][n] = (job.bias ? job.bias[n] : 0.f) + (job.bias_img ? job.bias_img[img_h * N + n] : 0.f);
+                }
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const int img = (int)(m / p.g.R);
@@ -289,7 +320,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
             const uint32_t trow = tmem_base + buf * 2 * N + hf * N + ((uint32_t)(q * 32) << 16);
             const bool ln = job.ln_gamma != nullptr;
             float mu = 0.f, rstd = 1.f;
-            if (ln) epi_ln_stats<N>(trow, bias_s[buf], job.ln_eps, mu, rstd);
+            if (ln) epi_ln_stats<N>(trow, bias_s[hf], job.ln_eps, mu, rstd);
             if ((p.bo_mode & 8) || (half && hf == 1)) {    // nothing to store (experiment switch / unused half of a 128-row tile)
                 tc_fence_before_sync();
                 if (lane == 0) mbar_arrive(&acc_empty[buf]);
@@ -306,7 +337,7 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     tc_fence_before_sync();
                     if (lane == 0) mbar_arrive(&acc_empty[buf]);
                 }
-                epi_chunk_staged(v, c, r, bias_s[buf], ln, mu, rstd, job.ln_gamma, job.ln_beta, stage, lane);   // gamma/beta: L1-resident broadcast loads
+                epi_chunk_staged(v, c, r, bias_s[hf], ln, mu, rstd, job.ln_gamma, job.ln_beta, stage, lane);   // gamma/beta: L1-resident broadcast loads
                 if (prof_on) w2 += clock64() - _ts;
             }
         }
@@ -356,8 +387,10 @@ int launch_conv_slab(GemmParams p, cudaStream_t st) {
     p.per_image = 0;
     for (int j = 0; j < p.n_jobs; ++j) {
         p.per_image |= p.jobs[j].w_img_stride != 0;                                   // per-image weights: per-image tiles
-        for (int sg = 0; sg < p.n_seg; ++sg) p.per_image |= ((p.tap1_mask >> sg) & 1) && p.jobs[j].t1_img_stride[sg] != 0;
     }
+    p.pimg_mask = 0;
+    for (int sg = 0; sg < p.n_seg; ++sg)
+        if (((p.tap1_mask >> sg) & 1) && p.jobs[0].t1_img_stride[sg] != 0) p.pimg_mask |= 1 << sg;
     if (p.tap1_mask && (p.n != 128 || p.n_taps != 9 || (p.tap1_mask & 1))) {
         set_error("conv_slab: centre-tap segments need a 3x3, N=128 launch whose first segment is a full 3x3");
         return BMC_ERR_ARG;
