@@ -507,12 +507,15 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
 // (4 x 8 register tile: 12 shared-memory float4 loads per 128 FMAs).
 constexpr int kFoldRows = 32;
 constexpr int kFoldLd = 132;              // Wv row pitch in floats: 16-byte aligned, rows 4 banks apart
-__global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
+constexpr int kFoldThreads = 256;
+constexpr int kFoldRpt = kFoldRows / (kFoldThreads / 16);     // rows per thread (2)
+__global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
     extern __shared__ __align__(16) float fsm[];
     float* Wv = fsm;                                  // [128][132]: Wv[c'][i]
     float* Gs = fsm + 128 * kFoldLd;                  // [32][128]: G rows, later P rows
     __shared__ float s_bv[128], s_s[kFoldRows];
     constexpr int kBlocks = 128 / kFoldRows;
+    const long long tk0 = clock64();
     const int rb = blockIdx.x % kBlocks;
     const int k = (blockIdx.x / kBlocks) & 1;
     const int img = blockIdx.x / (2 * kBlocks);
@@ -525,10 +528,12 @@ __global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
     const int n_slots = c_b - c_a + 1;
     // All global reads are issued up front (they are pure latency: ~10 dependent L2 round trips otherwise).
     // Wv[c'][i] from the chunk-major fp16 matrix: row wv_row + (i/64)*128 + c', column i%64 (8 values per load)
-    uint4 wraw[16];
+    constexpr int kWl = 128 * 16 / kFoldThreads;      // Wv uint4 loads per thread
+    constexpr int kGl = kFoldRows * 32 / kFoldThreads;   // G float4 positions per thread
+    uint4 wraw[kWl];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const int idx = tid + 128 * u, cp = idx >> 4, i8 = (idx & 15) * 8;
+    for (int u = 0; u < kWl; ++u) {
+        const int idx = tid + kFoldThreads * u, cp = idx >> 4, i8 = (idx & 15) * 8;
         wraw[u] = *reinterpret_cast<const uint4*>(p.w_base + ((long)p.wv_row[k] + (i8 >> 6) * 128 + cp) * 64 + (i8 & 63));
     }
     float s_val = 0.f;
@@ -543,58 +548,60 @@ __global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
     }
     {   // G rows summed over the partial slots in a fixed order; 8 positions per thread, 3 slots in flight
         const float* __restrict__ gp = p.g_partial + (((long)slot_a * 2 + k) * 128 + rb * kFoldRows) * 128;
-        float4 a[8];
+        float4 a[kGl];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int s = 0; s < n_slots; s += 3) {
-            float4 t[3][8];
+        for (int u = 0; u < kGl; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n_slots; s += 4) {
+            float4 t[4][kGl];
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
+            for (int d = 0; d < 4; ++d)
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
-                    t[d][u] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(gp + (long)(s + d) * 2 * 128 * 128 + (tid + 128 * u) * 4)
+                for (int u = 0; u < kGl; ++u)
+                    t[d][u] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(gp + (long)(s + d) * 2 * 128 * 128 + (tid + kFoldThreads * u) * 4)
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int d = 0; d < 3; ++d)
+            for (int d = 0; d < 4; ++d)
 #pragma unroll
-                for (int u = 0; u < 8; ++u) { a[u].x += t[d][u].x; a[u].y += t[d][u].y; a[u].z += t[d][u].z; a[u].w += t[d][u].w; }
+                for (int u = 0; u < kGl; ++u) { a[u].x += t[d][u].x; a[u].y += t[d][u].y; a[u].z += t[d][u].z; a[u].w += t[d][u].w; }
         }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) *reinterpret_cast<float4*>(Gs + (tid + 128 * u) * 4) = a[u];
+        for (int u = 0; u < kGl; ++u) *reinterpret_cast<float4*>(Gs + (tid + kFoldThreads * u) * 4) = a[u];
     }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        const int idx = tid + 128 * u, cp = idx >> 4, i8 = (idx & 15) * 8;
+    for (int u = 0; u < kWl; ++u) {
+        const int idx = tid + kFoldThreads * u, cp = idx >> 4, i8 = (idx & 15) * 8;
         const float2 a = unpack_act2(wraw[u].x), b2 = unpack_act2(wraw[u].y), c2 = unpack_act2(wraw[u].z), d = unpack_act2(wraw[u].w);
         float* dst = Wv + cp * kFoldLd + i8;
         *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b2.x, b2.y);
         *reinterpret_cast<float4*>(dst + 4) = make_float4(c2.x, c2.y, d.x, d.y);
     }
-    s_bv[tid] = p.bv[k][tid];
+    if (tid < 128) s_bv[tid] = p.bv[k][tid];
     if (tid < kFoldRows) s_s[tid] = s_val;
     __syncthreads();
+    const long long tk1 = clock64();
     const int rg = tid >> 4, cg = tid & 15;
     // logits: rows 4 rg + a, columns c' = cg + 16 j
-    float acc[4][8];
+    float acc[kFoldRpt][8];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < kFoldRpt; ++a)
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[a][j] = 0.f;
     for (int i = 0; i < 128; i += 4) {
-        float4 gv[4];
+        float4 gv[kFoldRpt];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) gv[a] = *reinterpret_cast<const float4*>(Gs + (rg * 4 + a) * 128 + i);
+        for (int a = 0; a < kFoldRpt; ++a) gv[a] = *reinterpret_cast<const float4*>(Gs + (rg * kFoldRpt + a) * 128 + i);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float4 w = *reinterpret_cast<const float4*>(Wv + (cg + 16 * j) * kFoldLd + i);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) acc[a][j] += gv[a].x * w.x + gv[a].y * w.y + gv[a].z * w.z + gv[a].w * w.w;
+            for (int a = 0; a < kFoldRpt; ++a) acc[a][j] += gv[a].x * w.x + gv[a].y * w.y + gv[a].z * w.z + gv[a].w * w.w;
         }
     }
-    float bsum[4];
+    const long long tk2 = clock64();
+    float bsum[kFoldRpt];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const float sc = s_s[rg * 4 + a];
+    for (int a = 0; a < kFoldRpt; ++a) {
+        const float sc = s_s[rg * kFoldRpt + a];
         float mx = -INFINITY;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -615,25 +622,26 @@ __global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
     }
     __syncthreads();                                   // every thread is done reading the G rows
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < kFoldRpt; ++a)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) Gs[(rg * 4 + a) * 128 + cg + 16 * j] = acc[a][j];       // P
+        for (int j = 0; j < 8; ++j) Gs[(rg * kFoldRpt + a) * 128 + cg + 16 * j] = acc[a][j];       // P
     __syncthreads();
+    const long long tk3 = clock64();
     // M[c][i] = sum_c' P[c][c'] Wv[c'][i] for i = cg*4 + 64 u + (0..3)
-    float4 m[4][2];
+    float4 m[kFoldRpt][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) { m[a][0] = make_float4(0.f, 0.f, 0.f, 0.f); m[a][1] = m[a][0]; }
+    for (int a = 0; a < kFoldRpt; ++a) { m[a][0] = make_float4(0.f, 0.f, 0.f, 0.f); m[a][1] = m[a][0]; }
     for (int cp = 0; cp < 128; cp += 4) {
-        float4 pr[4];
+        float4 pr[kFoldRpt];
 #pragma unroll
-        for (int a = 0; a < 4; ++a) pr[a] = *reinterpret_cast<const float4*>(Gs + (rg * 4 + a) * 128 + cp);
+        for (int a = 0; a < kFoldRpt; ++a) pr[a] = *reinterpret_cast<const float4*>(Gs + (rg * kFoldRpt + a) * 128 + cp);
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
                 const float4 w = *reinterpret_cast<const float4*>(Wv + (cp + d) * kFoldLd + cg * 4 + 64 * u);
 #pragma unroll
-                for (int a = 0; a < 4; ++a) {
+                for (int a = 0; a < kFoldRpt; ++a) {
                     const float pv = d == 0 ? pr[a].x : (d == 1 ? pr[a].y : (d == 2 ? pr[a].z : pr[a].w));
                     m[a][u].x += pv * w.x; m[a][u].y += pv * w.y; m[a][u].z += pv * w.z; m[a][u].w += pv * w.w;
                 }
@@ -643,8 +651,8 @@ __global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
     const int pair = inst * 2 + k;
     act_t* mb = p.m_base + ((long)pair * p.B + b) * 256 * 64;
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int c = rb * kFoldRows + rg * 4 + a;
+    for (int a = 0; a < kFoldRpt; ++a) {
+        const int c = rb * kFoldRows + rg * kFoldRpt + a;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             uint2 o2;
@@ -653,6 +661,203 @@ __global__ void __launch_bounds__(128) att_fold(const FoldParams p) {
             *reinterpret_cast<uint2*>(mb + (u * 128 + c) * 64 + cg * 4) = o2;      // i = cg*4 + 64 u: chunk u, column cg*4
         }
         if (cg == 0) p.bias_img[((long)pair * p.B + b) * 128 + c] = bsum[a];
+    }
+    if (p.dbg && tid == 0 && (blockIdx.x == 0 || blockIdx.x == 77)) {
+        const long long tk4 = clock64();
+        printf("foldprof cta %d: load %lld gemm1 %lld softmax %lld gemm2+store %lld (n_slots %d)\n", blockIdx.x, tk1 - tk0, tk2 - tk1, tk3 - tk2, tk4 - tk3, n_slots);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// att_fold_tc: the same fold on the tensor core.  One CTA per (instance, image, k, block of 32 rows c):
+//   rows live in TMEM lanes 0..31 of M=128 MMAs (lanes 32..127 compute on don't-care rows).
+//   G is split into two fp16 terms (hi + lo, after an exact 2^-8 scaling that keeps sums of
+//   thousands of pixels inside the fp16 range), so  att = (G_hi + G_lo) Wv^T  keeps ~22 bits.
+//   MMA 1: att  = G_hi Wv^T + G_lo Wv^T      A = G tiles (K-major, K = i), B = Wv (K-major rows c')
+//   warp 0: + s bv^T, * scale, row softmax (three passes over TMEM), P -> fp16 tile, bias' = P bv
+//   MMA 2: M    = P Wv                        A = P (K-major, K = c'),    B = Wv as [K = c'][N = i] (N-major)
+//   warp 0: M -> fp16 chunk-major rows, 128 contiguous bytes per (row, chunk)
+constexpr int kFoldTcRows = 32;
+constexpr int kFoldTcThreads = 128;
+constexpr int kFoldTcSmem = 3 * kTensBytes + 1024;     // Wv, G_hi (later P), G_lo
+constexpr float kGScale = 1.f / 256.f;
+
+// fp16 element (row r, 4 consecutive columns i..i+3) of a [128 x 128] K-major SWIZZLE_128B tile
+__device__ __forceinline__ uint8_t* tile_addr4(uint8_t* tile, int r, int i) {
+    return tile + (i >> 6) * kHalfBytes + r * 128 + ((((i & 63) >> 3) ^ (r & 7)) << 4) + ((i & 7) << 1);
+}
+
+__global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_constant__ FoldParams p, const __grid_constant__ CUtensorMap map_w) {
+    extern __shared__ __align__(1024) uint8_t smem_dyn[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+    uint8_t* s_wv = smem;
+    uint8_t* s_gh = smem + kTensBytes;                 // G_hi, then P
+    uint8_t* s_gl = smem + 2 * kTensBytes;
+    __shared__ uint64_t bar_w, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ float s_bv[128], s_s[kFoldTcRows];
+    constexpr int kBlocks = 128 / kFoldTcRows;
+    const int rb = blockIdx.x % kBlocks;
+    const int k = (blockIdx.x / kBlocks) & 1;
+    const int img = blockIdx.x / (2 * kBlocks);
+    const int inst = img / p.B, b = img - inst * p.B;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tpc = p.tiles_per_cta, tpi = p.tiles_per_img;
+    const int c_a = (img * tpi) / tpc, c_b = ((img + 1) * tpi - 1) / tpc;
+    const int slot_a = segs_before(c_a, tpc, tpi, p.lcm) + (img - (c_a * tpc) / tpi);
+    const int n_slots = c_b - c_a + 1;
+
+    if (tid == 0) {
+        mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+        mbar_expect_tx(&bar_w, kTensBytes);
+        const int row = k == 0 ? p.wv_row[0] : p.wv_row[1];
+        tma_load_2d(s_wv, &map_w, &bar_w, 0, row);
+        tma_load_2d(s_wv + kHalfBytes, &map_w, &bar_w, 0, row + 128);
+    }
+    if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+    // G rows [32 rb, 32 rb + 32) summed over the partial slots (fixed order), split hi / lo, into tile rows 0..31
+    {
+        const float* __restrict__ gp = p.g_partial + (((long)slot_a * 2 + k) * 128 + rb * kFoldTcRows) * 128;
+        float4 a[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int s = 0; s < n_slots; s += 3) {
+            float4 t[3][8];
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+                    t[d][u] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(gp + (long)(s + d) * 2 * 128 * 128 + (tid + kFoldTcThreads * u) * 4)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { a[u].x += t[d][u].x; a[u].y += t[d][u].y; a[u].z += t[d][u].z; a[u].w += t[d][u].w; }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int idx = tid + kFoldTcThreads * u, r = idx >> 5, i = (idx & 31) * 4;
+            const float g[4] = {a[u].x * kGScale, a[u].y * kGScale, a[u].z * kGScale, a[u].w * kGScale};
+            float h[4], l[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { h[e] = from_act(to_act(g[e])); l[e] = g[e] - h[e]; }
+            *reinterpret_cast<uint2*>(tile_addr4(s_gh, r, i)) = make_uint2(pack_act2(h[0], h[1]), pack_act2(h[2], h[3]));
+            *reinterpret_cast<uint2*>(tile_addr4(s_gl, r, i)) = make_uint2(pack_act2(l[0], l[1]), pack_act2(l[2], l[3]));
+        }
+    }
+    s_bv[tid] = (k == 0 ? p.bv[0] : p.bv[1])[tid];
+    if (tid < kFoldTcRows) {
+        float sv = 0.f;
+        const float* __restrict__ sp = p.s_partial + (long)slot_a * 256 + k * 128 + rb * kFoldTcRows + tid;
+        for (int s = 0; s < n_slots; ++s) sv += sp[(long)s * 256];
+        s_s[tid] = sv;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t hi = umma_desc_hi_sw128(1024);
+    constexpr uint32_t half_units = kHalfBytes >> 4;
+    if (tid == 0) {
+        mbar_wait(&bar_w, 0);
+        tc_fence_after_sync();
+        constexpr uint32_t idesc = umma_idesc_f16(128, 128, false, false);
+        const uint32_t w_lo = umma_desc_lo(smem_u32(s_wv), 16);
+        const uint32_t g_lo[2] = {umma_desc_lo(smem_u32(s_gh), 16), umma_desc_lo(smem_u32(s_gl), 16)};
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma_f16(tmem, umma_desc(g_lo[t] + c * half_units + ks * 2, hi), umma_desc(w_lo + c * half_units + ks * 2, hi), idesc,
+                             (t | c | ks) ? 1u : 0u);
+        umma_commit(&bar_mma);
+    }
+    float bsum = 0.f;
+    if (warp == 0) {
+        // rows 0..31 = TMEM lanes 0..31: only warp 0 may read them
+        mbar_wait(&bar_mma, 0);
+        tc_fence_after_sync();
+        const float sc = s_s[lane];
+        const float k_att = p.scale / kGScale;         // undo the 2^-8 scaling of G together with nf^-0.5
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale);
+        }
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem + c * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum += expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx);
+        }
+        const float inv = 1.f / sum;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem + c * 32, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                f[j] = expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx) * inv;
+                bsum += f[j] * s_bv[c * 32 + j];
+            }
+            store_tile_row32(s_gh, lane, c, f);        // P row (the first MMA group has retired: its tiles are free)
+        }
+        fence_proxy_async_smem();
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    tc_fence_after_sync();
+    if (tid == 0) {
+        // M[c][i] = sum_c' P[c][c'] Wv[c'][i]: B is the Wv tile read as [K = c' rows][N = i columns]
+        constexpr uint32_t idesc2 = umma_idesc_f16(128, 128, false, true);
+        const uint32_t p_lo = umma_desc_lo(smem_u32(s_gh), 16);
+        const uint32_t w_mn = umma_desc_lo(smem_u32(s_wv), kHalfBytes);
+#pragma unroll
+        for (int s8 = 0; s8 < 8; ++s8)                 // K = 16 rows c' per slice: 2048 B down the Wv tile, 32 B along the P row
+            umma_f16(tmem + 128, umma_desc(p_lo + (s8 >> 2) * half_units + (s8 & 3) * 2, hi), umma_desc(w_mn + s8 * 128, hi), idesc2,
+                     s8 ? 1u : 0u);
+        umma_commit(&bar_mma);
+    }
+    if (warp == 0) {
+        mbar_wait(&bar_mma, 1);
+        tc_fence_after_sync();
+        const int pair = inst * 2 + k;
+        const int c_row = rb * kFoldTcRows + lane;
+        act_t* mb = p.m_base + ((long)pair * p.B + b) * 256 * 64;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem + 128 + c * 32, v);
+            tmem_ld_wait();
+            // columns i = 32 c .. 32 c + 31 -> chunk c / 2, 64 contiguous bytes of row c_row
+            uint4* dst = reinterpret_cast<uint4*>(mb + ((c >> 1) * 128 + c_row) * 64 + (c & 1) * 32);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                dst[u] = make_uint4(pack_act2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
+                                    pack_act2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
+                                    pack_act2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
+                                    pack_act2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
+        }
+        p.bias_img[((long)pair * p.B + b) * 128 + c_row] = bsum;
+        tc_fence_before_sync();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after_sync();
+        tmem_dealloc(tmem, 256);
     }
 }
 
@@ -707,6 +912,17 @@ int launch_bie_front(const BieFrontParams& p, cudaStream_t st) {
     return BMC_OK;
 }
 
+int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        BMC_CUDA(cudaFuncSetAttribute(att_fold_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldTcSmem));
+        configured = true;
+    }
+    att_fold_tc<<<p.n_inst * p.B * 2 * (128 / kFoldTcRows), kFoldTcThreads, kFoldTcSmem, st>>>(p, map_w);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
 int launch_att_fold(const FoldParams& p, cudaStream_t st) {
     const int smem = (128 * kFoldLd + kFoldRows * 128) * (int)sizeof(float);
     static bool configured = false;
@@ -714,7 +930,11 @@ int launch_att_fold(const FoldParams& p, cudaStream_t st) {
         BMC_CUDA(cudaFuncSetAttribute(att_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = true;
     }
-    att_fold<<<p.n_inst * p.B * 2 * (128 / kFoldRows), 128, smem, st>>>(p);
+    static int dbg = -1, calls = 0;
+    if (dbg < 0) dbg = getenv("BMC_FOLD_PROF") ? 1 : 0;
+    FoldParams q = p;
+    q.dbg = dbg && ++calls == 8;
+    att_fold<<<p.n_inst * p.B * 2 * (128 / kFoldRows), kFoldThreads, smem, st>>>(q);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

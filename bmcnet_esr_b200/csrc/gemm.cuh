@@ -31,6 +31,7 @@ struct GemmJobDev {
     int a_ld[kMaxSeg];
     long a_rows[kMaxSeg];
     int w_map;
+    int w_map64;               // same weights behind a [64 rows x 64] box (pair kernel: each CTA loads half a tile), or 0
     const act_t* w_ptr;
     int w_rows;                // rows per K chunk of the weight matrix behind w_map / w_ptr
     int w_row_base;
@@ -72,10 +73,12 @@ struct alignas(64) GemmParams {
     int tiles_per_img;         // R / 128
     // slab kernel (gemm_slab.cu); filled in by its launcher
     int slab_lead, slab_boxes, bo_mode;
+    int abox_rows;             // rows per TMA box of the a_map64 maps (slab_box_rows(): few large boxes, TMA cost is per op)
     int per_image;             // tiles never straddle images (per-image weights)
     // tile schedule: `n_full` 256-row tiles, then `n_half` 128-row tiles (the odd half at the end of every
     // image in per-image mode), the halves going to the CTAs that got one full tile less
     int n_full, n_half, full_per_img;
+    int pairs_per_job;         // pair kernel (gemm_pair.cu): 512-row pair tiles per job
     long long* prof;           // optional per-CTA cycle counters (tools/gpu_diag.py slabprof), else NULL
 };
 
@@ -132,9 +135,11 @@ struct FoldParams {
     float scale;
     act_t* m_base;                         // per-image matrices: rows pair*B*256 + b*256 + chunk*128 + c, pair = inst*2 + k
     float* bias_img;                       // [pair][B][128]
+    int dbg;                               // BMC_FOLD_PROF: print phase cycle counts
 };
 int launch_bie_front(const BieFrontParams& p, cudaStream_t st);
-int launch_att_fold(const FoldParams& p, cudaStream_t st);
+int launch_att_fold(const FoldParams& p, cudaStream_t st);                                   // SIMT version (BMC_FOLD_SIMT=1)
+int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream_t st);     // tensor-core version
 int bie_front_grid(int total_tiles);
 int bie_front_slots(int total_tiles, int tiles_per_img);
 int bie_front_lcm(int tiles_per_cta, int tiles_per_img);
@@ -142,6 +147,9 @@ int bie_front_lcm(int tiles_per_cta, int tiles_per_img);
 // Launchers (host).  `impl`: 0 = tcgen05/TMA (slab kernel when it applies, else the per-tap
 // kernel), 1 = SIMT cross-check, 2 = force the per-tap tcgen05 kernel.
 bool slab_supported(const GemmParams& p);
+int slab_box_rows(const Geom& g, int n_taps);   // TMA box height the slab kernels expect behind a_map64
+bool pair_supported(const GemmParams& p);
+int launch_conv_pair(GemmParams p, cudaStream_t st);
 int launch_conv_slab(GemmParams p, cudaStream_t st);
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st);
 int launch_att(const AttParams& p, int impl, cudaStream_t st);

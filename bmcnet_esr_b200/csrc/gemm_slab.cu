@@ -143,12 +143,13 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
                     const CUtensorMap* map = &p.maps[job.a_map64[s]];
                     const bool mix = (tap1_mask >> s) & 1;   // centre tap only: just the tile's own 256 rows
                     const int row0 = job.a_row_base[s] + m0 - (mix ? 0 : p.slab_lead);
-                    const int boxes = mix ? kBM / kBoxRows : p.slab_boxes;
-                    if (lane == 0) mbar_expect_tx(&a_full[st], boxes * kBoxBytes);
+                    const int abox = p.abox_rows;                                       // rows per TMA op
+                    const int boxes = ((mix ? kBM : p.slab_boxes * kBoxRows) + abox - 1) / abox;
+                    if (lane == 0) mbar_expect_tx(&a_full[st], boxes * abox * 128);
                     __syncwarp();
                     if (lane < boxes)
-                        tma_load_2d(dst + lane * kBoxBytes, map, &a_full[st], job.a_col_base[s] + as_chunk[as] * kChunkK,
-                                    row0 + lane * kBoxRows);
+                        tma_load_2d(dst + lane * abox * 128, map, &a_full[st], job.a_col_base[s] + as_chunk[as] * kChunkK,
+                                    row0 + lane * abox);
                 }
             }
             if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 0] = w0; p.prof[blockIdx.x * 16 + 1] = clock64() - t_begin; }
@@ -381,9 +382,19 @@ bool slab_supported(const GemmParams& p) {
     return smem + 2048 <= 227 * 1024;
 }
 
+// Rows per TMA box for the activation slabs: the slab (a multiple of 64 rows) in as few equal boxes of
+// <= 256 rows as possible -- the TMA engine's cost is per operation, not per byte.
+int slab_box_rows(const Geom& g, int n_taps) {
+    const int lead = n_taps == 9 ? g.Wp + 1 : 0;
+    const int rows = (kBM + 2 * lead + kBoxRows - 1) / kBoxRows * kBoxRows;
+    const int n_ops = (rows + 255) / 256;
+    return (rows % n_ops == 0 && (rows / n_ops) % 8 == 0) ? rows / n_ops : kBoxRows;
+}
+
 int launch_conv_slab(GemmParams p, cudaStream_t st) {
     p.slab_lead = p.n_taps == 9 ? p.g.Wp + 1 : 0;
     p.slab_boxes = (kBM + 2 * p.slab_lead + kBoxRows - 1) / kBoxRows;
+    if (p.abox_rows <= 0) p.abox_rows = kBoxRows;
     p.per_image = 0;
     for (int j = 0; j < p.n_jobs; ++j) {
         p.per_image |= p.jobs[j].w_img_stride != 0;                                   // per-image weights: per-image tiles

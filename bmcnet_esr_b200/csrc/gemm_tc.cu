@@ -262,11 +262,14 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
 int launch_conv_gemm_simt(const GemmParams& p, cudaStream_t st);
 int launch_att_simt(const AttParams& p, cudaStream_t st);
 
+static bool use_pair_ok(const GemmParams& p) { return p.jobs[0].a_map64[0] >= 0 && slab_supported(p) && pair_supported(p); }
+
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
     if (p.tap1_mask && (impl != 0 || p.jobs[0].a_map64[0] < 0 || !slab_supported(p))) {
         set_error("conv_gemm: centre-tap segments exist only in the slab kernel");
         return BMC_ERR_UNSUPPORTED;
     }
+    if (impl == 0 && use_pair_ok(p)) return launch_conv_pair(p, st);
     if (p.tap1_mask) return launch_conv_slab(p, st);
     if (impl == 1) return launch_conv_gemm_simt(p, st);
     static int use_slab = -1;

@@ -167,7 +167,8 @@ struct bmc_model {
     bool fused = true;                     // product plan: fused BIE 1x1 / attention section (bie_fused.cu)
     bool allow_fused = true;
     char* ws = nullptr;
-    CUtensorMap map_act, map_att, map_mi, map_mi64, map_w128, map_w32, map_p;
+    CUtensorMap map_act, map_att, map_slab, map_mi, map_mi64, map_w128, map_w64, map_w32, map_p;
+    int abox = 64;                         // rows per TMA box of map_slab / map_mi64 (slab_box_rows)
     // plan
     std::vector<Op> ops;
     std::vector<int> free_slots;
@@ -302,8 +303,11 @@ struct Builder {
         p.maps[0] = m->map_act; p.maps[1] = m->map_mi;
         p.maps[2] = (n == 32) ? m->map_w32 : m->map_w128;
         p.maps[3] = m->map_p;
-        p.maps[4] = m->map_att;                 // act arena, 64-row boxes (slab kernel)
+        p.maps[4] = m->map_slab;                // act arena, slab boxes (slab / pair kernels)
+        p.abox_rows = taps == 9 ? m->abox : 64;
         p.maps[5] = m->map_mi64;
+        p.maps[6] = m->map_w64;
+        p.maps[7] = m->map_att;                 // act arena, 64-row boxes (1x1 launches of the unfused plan)
         p.n_jobs = (int)jobs.size();
         const int n_plain = (int)jobs[0].segs.size();
         p.n_seg = n_plain + (jobs[0].mix_slot >= 0) + (jobs[0].ident_slot >= 0);
@@ -333,14 +337,14 @@ struct Builder {
                 if (src.kind == 1) {
                     d.a_map[s] = 1; d.a_map64[s] = 5; d.a_row_base[s] = 0; d.a_ptr[s] = m->mi_ptr(); d.a_ld[s] = 64; d.a_rows[s] = g.rows();
                 } else {
-                    d.a_map[s] = 0; d.a_map64[s] = 4; d.a_row_base[s] = (int)(src.slot * g.rows());
+                    d.a_map[s] = 0; d.a_map64[s] = taps == 9 ? 4 : 7; d.a_row_base[s] = (int)(src.slot * g.rows());
                     d.a_ptr[s] = m->slot_ptr(0); d.a_ld[s] = 128; d.a_rows[s] = (long)m->n_slots * g.rows();
                 }
                 d.a_col_base[s] = 0;
             }
             if (js.weight >= 0) {
                 const WeightSpec& w = m->weights[js.weight];
-                d.w_map = 2; d.w_ptr = m->w_dev; d.w_rows = w.n_out; d.w_row_base = w.row_base; d.w_img_stride = 0;
+                d.w_map = 2; d.w_map64 = n == 128 ? 6 : 0; d.w_ptr = m->w_dev; d.w_rows = w.n_out; d.w_row_base = w.row_base; d.w_img_stride = 0;
                 d.bias = m->f32_dev + w.bias_off;
             } else {
                 d.w_map = 3; d.w_ptr = m->p_ptr(); d.w_rows = 128;
@@ -670,7 +674,11 @@ int launch_op(bmc_model* m, const Op& op, cudaStream_t st) {
     if (op.kind == Op::kGemm) return launch_conv_gemm(op.gp, m->simt, st);
     if (op.kind == Op::kAtt) return launch_att(op.ap, m->simt, st);
     if (op.kind == Op::kBieFront) return launch_bie_front(op.fp, st);
-    if (op.kind == Op::kFold) return launch_att_fold(op.dp, st);
+    if (op.kind == Op::kFold) {
+        static int simt_fold = -1;
+        if (simt_fold < 0) { const char* e = getenv("BMC_FOLD_SIMT"); simt_fold = e ? atoi(e) : 0; }
+        return simt_fold ? launch_att_fold(op.dp, st) : launch_att_fold_tc(op.dp, m->map_w128, st);
+    }
     return launch_att_softmax(op.sp, st);
 }
 
@@ -684,7 +692,7 @@ int run_ops(bmc_model* m, cudaStream_t st) {
         if (op.kind == Op::kGemm) rc = launch_conv_gemm(op.gp, m->simt, st);
         else if (op.kind == Op::kAtt) rc = launch_att(op.ap, m->simt, st);
         else if (op.kind == Op::kBieFront) rc = launch_bie_front(op.fp, st);
-        else if (op.kind == Op::kFold) rc = launch_att_fold(op.dp, st);
+        else if (op.kind == Op::kFold) rc = launch_op(m, op, st);
         else rc = launch_att_softmax(op.sp, st);
         if (rc) return rc;
     }
@@ -817,6 +825,8 @@ extern "C" BMC_EXPORT int bmc_model_load_state_dict(bmc_model_t* m, const char* 
     }
     int rc = make_tmap_2d_act(&m->map_w128, m->w_dev, (uint64_t)m->w_rows_total, 64, 128, 64);
     if (rc) return rc;
+    rc = make_tmap_2d_act(&m->map_w64, m->w_dev, (uint64_t)m->w_rows_total, 64, 64, 64);
+    if (rc) return rc;
     rc = make_tmap_2d_act(&m->map_w32, m->w_dev, (uint64_t)m->w_rows_total, 64, 32, 64);
     if (rc) return rc;
     m->loaded = true;
@@ -896,8 +906,10 @@ extern "C" BMC_EXPORT int bmc_model_bind_workspace(bmc_model_t* m, void* workspa
     const uint64_t rows = (uint64_t)m->g.rows();
     int rc = make_tmap_2d_act(&m->map_act, m->slot_ptr(0), rows * m->n_slots, 128, 128, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_att, m->slot_ptr(0), rows * m->n_slots, 128, 64, 64);
+    m->abox = slab_box_rows(m->g, 9);
+    if (!rc) rc = make_tmap_2d_act(&m->map_slab, m->slot_ptr(0), rows * m->n_slots, 128, (uint32_t)m->abox, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_mi, m->mi_ptr(), rows, 64, 128, 64);
-    if (!rc) rc = make_tmap_2d_act(&m->map_mi64, m->mi_ptr(), rows, 64, 64, 64);
+    if (!rc) rc = make_tmap_2d_act(&m->map_mi64, m->mi_ptr(), rows, 64, (uint32_t)m->abox, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_p, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128, 64);
     if (rc) return rc;
     m->dry = false;
@@ -1015,6 +1027,7 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
         return BMC_OK;
     };
     bool maps64_ok = true;
+    p.abox_rows = slab_box_rows(g, taps);
     for (int j = 0; j < n_jobs; ++j) {
         const bmc_gemm_job_t& js = jobs[j];
         GemmJobDev& d = p.jobs[j];
@@ -1034,6 +1047,13 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
         int rc = get_map(js.w, w_total, 64, (uint32_t)n, &d.w_map);
         if (rc) return rc;
         BMC_REQUIRE(d.w_map >= 0, "conv_gemm: more than %d distinct operand tensors in one call", kMaxMaps);
+        d.w_map64 = 0;
+        if (n == 128 && js.w_img_stride == 0) {                     // pair kernel: half-tile boxes of the same weights
+            int idx = -1;
+            rc = get_map(js.w, w_total, 64, 64, &idx);
+            if (rc) return rc;
+            d.w_map64 = idx > 0 ? idx : 0;
+        }
         d.w_ptr = static_cast<const act_t*>(js.w); d.w_rows = js.w_rows;
         d.w_row_base = js.w_row_base; d.w_img_stride = js.w_img_stride;
         d.bias = js.bias; d.relu = js.relu;
@@ -1044,7 +1064,7 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
     // 64-row-box descriptors for the slab kernel, if they still fit; otherwise the per-tap kernel runs
     for (int j = 0; j < n_jobs && maps64_ok; ++j)
         for (int s = 0; s < p.n_seg && maps64_ok; ++s) {
-            int rc = get_map(jobs[j].a[s], (uint64_t)jobs[j].a_rows[s], (uint64_t)jobs[j].a_ch[s], 64, &p.jobs[j].a_map64[s]);
+            int rc = get_map(jobs[j].a[s], (uint64_t)jobs[j].a_rows[s], (uint64_t)jobs[j].a_ch[s], (uint32_t)p.abox_rows, &p.jobs[j].a_map64[s]);
             if (rc) return rc;
             if (p.jobs[j].a_map64[s] < 0) maps64_ok = false;
         }

@@ -102,8 +102,10 @@ __global__ void __launch_bounds__(128, 1) bench(float* out, long long* cyc, int 
     constexpr uint32_t hi = desc_hi(1024);
     long long t = 0;
     const bool dual = (mode & 64) != 0;                    // two issuing warps, one accumulator each
-    if ((threadIdx.x == 0 || (dual && threadIdx.x == 32)) && rank == 0) {
-        const int who = threadIdx.x >> 5;
+    const bool split = (mode & 128) != 0;                  // dual issuers, the second one in the peer CTA (CG == 2)
+    const bool issuer = split ? (threadIdx.x == 0) : ((threadIdx.x == 0 || (dual && threadIdx.x == 32)) && rank == 0);
+    if (issuer) {
+        const int who = split ? rank : (threadIdx.x >> 5);
         const uint32_t a_lo = desc_lo(smem_u32(sa) + row_shift * 128, 16), b_lo = desc_lo(smem_u32(sb), 16);
         const int period = (mode & 32) ? 4 : 2;            // wait / commit every 16 or 8 MMAs
         const long long t0 = clock64();
@@ -119,13 +121,13 @@ __global__ void __launch_bounds__(128, 1) bench(float* out, long long* cyc, int 
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 mma<CG>(acc, desc(a_it + k * 2, hi), desc(b_lo + k * 2, hi), idesc, (it > 1 || k) ? 1u : 0u);
-            if ((mode & 1) && (it % period) == period - 1) commit<1>(&ring[(it >> 1) & 7]);
+            if ((mode & 1) && (it % period) == period - 1) { if (mode & 256) commit<CG>(&ring[(it >> 1) & 7]); else commit<1>(&ring[(it >> 1) & 7]); }
         }
         commit<CG>(who ? &done2 : &bar);
         mbar_wait(who ? &done2 : &bar, 0);
         t = clock64() - t0;
         if (who == 0) cyc[cluster] = t;
-    } else if (threadIdx.x == 0) {
+    } else if (threadIdx.x == 0 && !split) {
         mbar_wait(&bar, 0);                               // peer CTA: multicast commit arrives here too
     }
     __syncthreads();
@@ -184,7 +186,7 @@ void run(int clusters, int row_shift, int mode = 0) {
         } else if (iters > 1) {
             std::vector<long long> c(clusters);
             cudaMemcpy(c.data(), cyc, clusters * 8, cudaMemcpyDeviceToHost);
-            const double per = (double)c[0] / (iters * 4) / ((mode & 64) ? 2 : 1);
+            const double per = (double)c[0] / (iters * 4) / ((mode & (64 | 128)) ? 2 : 1);
             printf("mode=%2d ", mode);
             printf("CG=%d M=%d N=%3d clusters=%3d: %.1f cycles per MMA (K=16) -> %.0f MAC/clk/SM\n", CG, 128 * CG, N, clusters, per,
                    128.0 * N * 16 / per);
@@ -196,6 +198,7 @@ void run(int clusters, int row_shift, int mode = 0) {
 int main(int argc, char** argv) {
     if (argc > 1) {
         for (int mode : {0, 17, 17 + 32, 64, 64 + 17, 64 + 17 + 32, 64 + 31}) run<1, 128>(148, 0, mode);
+        for (int mode : {64 + 17, 256 + 64 + 17, 256 + 64 + 17 + 32, 256 + 17}) run<2, 128>(74, 0, mode);
         return 0;
     }
     run<1, 64>(1, 0);
