@@ -149,6 +149,8 @@ int bie_front_lcm(int tiles_per_cta, int tiles_per_img);
 bool slab_supported(const GemmParams& p);
 int slab_box_rows(const Geom& g, int n_taps);   // TMA box height the slab kernels expect behind a_map64
 bool pair_supported(const GemmParams& p);
+bool slabt_supported(const GemmParams& p);
+int launch_conv_slabt(GemmParams p, cudaStream_t st);
 int launch_conv_pair(GemmParams p, cudaStream_t st);
 int launch_conv_slab(GemmParams p, cudaStream_t st);
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st);

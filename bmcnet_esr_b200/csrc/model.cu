@@ -355,7 +355,7 @@ struct Builder {
             d.res_row_base = 0;
             d.out = js.out_slot >= 0 ? m->slot_ptr(js.out_slot) : nullptr;
             d.out_row_base = 0;
-            d.out_f32 = js.out_f32 ? m->a32_ptr() : (js.hid32 >= 0 ? m->hid32_ptr(js.hid32) : nullptr);
+            d.out_f32 = js.out_f32 ? m->a32_ptr() : nullptr;
             if (js.ln >= 0) {
                 d.ln_gamma = m->f32_dev + m->lns[js.ln].gamma_off;
                 d.ln_beta = m->f32_dev + m->lns[js.ln].beta_off;
@@ -968,7 +968,7 @@ extern "C" BMC_EXPORT int bmc_model_forward(bmc_model_t* m, const float* x, cons
     rc = run_plan(m, st);
     if (rc) return rc;
     for (int i = 0; i < nh; ++i) {
-        rc = launch_unpack_nchw_f32(m->hid32_ptr(i), m->g, 128, 128, hout[i], st);   // fp32 accumulators, not the 16-bit copy
+        rc = launch_unpack_nchw(m->slot_ptr(m->slot_h[i]), m->g, 128, 128, 0, hout[i], st);   // the 16-bit state, widened
         if (rc) return rc;
     }
     EmitParams ep;

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(128, 1) bench(float* out, long long* cyc, int 
     extern __shared__ __align__(1024) uint8_t raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
     __half* sa = (__half*)smem;                          // [128 + 16 rows][64]  (extra rows for the shifted view)
-    __half* sb = (__half*)(smem + (128 + 16) * 128);     // [N/CG rows][64]
+    __half* sb = (__half*)(smem + (128 + 16) * 128);     // [N/CG (+16) rows][64]
+    const int b_shift = (mode & 512) ? row_shift : 0;   // mode 512: the row shift applies to B instead of A
+    const int a_shift = (mode & 512) ? 0 : row_shift;
     __shared__ uint64_t bar, ring[8], done_bar, done2;
     __shared__ uint32_t tmem_s;
     const int rank = CG == 2 ? (int)cg::this_cluster().block_rank() : 0;
@@ -75,9 +77,9 @@ __global__ void __launch_bounds__(128, 1) bench(float* out, long long* cyc, int 
     constexpr int NB = N / CG;
     for (int i = threadIdx.x; i < (128 + 16) * 64; i += 128) {
         const int r = i / 64, k = i % 64;
-        put(sa, r, k, aval(rank * 128 + r - row_shift, k));           // row r of the slab = logical row r - shift
+        put(sa, r, k, aval(rank * 128 + r - a_shift, k));           // row r of the slab = logical row r - shift
     }
-    for (int i = threadIdx.x; i < NB * 64; i += 128) put(sb, i / 64, i % 64, bval(rank * NB + i / 64, i % 64));
+    for (int i = threadIdx.x; i < (NB + 16) * 64; i += 128) put(sb, i / 64, i % 64, bval(rank * NB + i / 64 - b_shift, i % 64));
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1); mbar_init(&done_bar, 1); mbar_init(&done2, 1);
         for (int i = 0; i < 8; ++i) mbar_init(&ring[i], 1);
@@ -106,7 +108,7 @@ __global__ void __launch_bounds__(128, 1) bench(float* out, long long* cyc, int 
     const bool issuer = split ? (threadIdx.x == 0) : ((threadIdx.x == 0 || (dual && threadIdx.x == 32)) && rank == 0);
     if (issuer) {
         const int who = split ? rank : (threadIdx.x >> 5);
-        const uint32_t a_lo = desc_lo(smem_u32(sa) + row_shift * 128, 16), b_lo = desc_lo(smem_u32(sb), 16);
+        const uint32_t a_lo = desc_lo(smem_u32(sa) + a_shift * 128, 16), b_lo = desc_lo(smem_u32(sb) + b_shift * 128, 16);
         const int period = (mode & 32) ? 4 : 2;            // wait / commit every 16 or 8 MMAs
         const long long t0 = clock64();
         for (int it = 0; it < iters; ++it) {
@@ -157,7 +159,7 @@ __global__ void __launch_bounds__(128, 1) bench(float* out, long long* cyc, int 
 
 template <int CG, int N>
 void run(int clusters, int row_shift, int mode = 0) {
-    const int smem = (128 + 16) * 128 + (N / CG) * 128 + 1024;
+    const int smem = (128 + 16) * 128 + (N / CG + 16) * 128 + 1024;
     auto kern = bench<CG, N>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     float* out; long long* cyc;
@@ -172,7 +174,7 @@ void run(int clusters, int row_shift, int mode = 0) {
         cudaError_t e = cudaLaunchKernelEx(&cfg, kern, out, cyc, iters, row_shift, mode);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         if (e != cudaSuccess) { printf("CG=%d N=%d: CUDA error %s\n", CG, N, cudaGetErrorString(e)); exit(1); }
-        if (iters == 1 && mode == 0) {
+        if (iters == 1 && (mode & ~512) == 0) {
             std::vector<float> h((size_t)CG * 128 * N);
             cudaMemcpy(h.data(), out, h.size() * 4, cudaMemcpyDeviceToHost);
             double maxerr = 0;
@@ -196,6 +198,11 @@ void run(int clusters, int row_shift, int mode = 0) {
 }
 
 int main(int argc, char** argv) {
+    if (argc > 1 && argv[1][0] == 'b') {
+        for (int sh : {0, 1, 3, 5, 8, 13}) run<1, 256>(1, sh, 512);
+        run<1, 256>(148, 3, 512);
+        return 0;
+    }
     if (argc > 1) {
         for (int mode : {0, 17, 17 + 32, 64, 64 + 17, 64 + 17 + 32, 64 + 31}) run<1, 128>(148, 0, mode);
         for (int mode : {64 + 17, 256 + 64 + 17, 256 + 64 + 17 + 32, 256 + 17}) run<2, 128>(74, 0, mode);
