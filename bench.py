@@ -158,8 +158,10 @@ def main():
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     model_kind, h, w, n_win, desc = WORKLOADS[args.workload]
     if args.batch <= 0:
-        # tiles per conv job = ceil(B * R / 256), R = roundup((H+2)(W+2), 128): 19 x 3968 / 256 = 295 ~ 2 x 148
-        args.batch = {'plain_nfs': 19, 'bmcnet_nfs': 19, 'bmcnet_eventzoom': 39}[args.workload]
+        # tiles per conv job = ceil(B * R / 256), R = roundup((H+2)(W+2), 128): multiples of 19 images give
+        # 19 x 3968 / 256 = 294.5 ~ 2 x 148 tiles per job (whole waves of the 148 SMs); larger batches amortise
+        # the per-launch prologue (measured: plain 20.0k / 22.3k / 23.3k frames/s at B = 19 / 38 / 57)
+        args.batch = {'plain_nfs': 57, 'bmcnet_nfs': 38, 'bmcnet_eventzoom': 78}[args.workload]
     config = {'workload': desc, 'batch_per_gpu': args.batch, 'lr_hw': [h, w], 'events_per_window': n_win,
               'windows_per_step_per_sequence': 2, 'sharding': 'independent sequences per GPU, no collective'}
 
@@ -316,10 +318,10 @@ def main():
     conv_flops = 2.0 * CONV_MAC_PER_PX * h * w * B * jobs
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     peak = peaks.get('bf16_tflops', 1590.0)
-    roofline = {'kernel': 'conv_slab_tc<128> (3x3 128->128, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
+    roofline = {'kernel': 'conv_slabt_tc (3x3 128->128 implicit GEMM, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
                 'us_per_launch': conv_ms * 1e3,
-                'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s'}
+                'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)'}
 
     # encoder kernel against HBM
     n_big = 200_000_000
@@ -337,7 +339,21 @@ def main():
     enc_ms = r0.elapsed_time(r1) / 5
     enc_gbs = (12.0 * n_big + 2 * h * w * 4) / (enc_ms * 1e-3) / 1e9
     hbm = peaks.get('hbm_gbs', 6650.0)
-    del xs, ys, ps
+    # time-interpolated voxels (events_to_voxel, 5 bins): 16 B/event (BASELINE metric "voxel encoding Mevents/s")
+    n_vox = 100_000_000
+    ts = torch.sort(torch.rand(n_vox, device=dev))[0]
+    xv, yv, pv = xs[:n_vox].contiguous(), ys[:n_vox].contiguous(), ps[:n_vox].contiguous()
+    for _ in range(2):
+        G.events_to_voxel(xv, yv, ts, pv, 5, sensor_size=(h, w))
+    torch.cuda.synchronize()
+    r0.record()
+    for _ in range(3):
+        G.events_to_voxel(xv, yv, ts, pv, 5, sensor_size=(h, w))
+    r1.record()
+    torch.cuda.synchronize()
+    vox_ms = r0.elapsed_time(r1) / 3
+    vox_gbs = (16.0 * n_vox + 5 * h * w * 4) / (vox_ms * 1e-3) / 1e9
+    del xs, ys, ps, xv, yv, pv, ts
 
     # ------------------------------------------------------------------ CPU baseline (bounded sample)
     cpu_fps, cpu_ms, cores = cpu_reference(model_kind, h, w, n_win, args.cpu_steps, 2)
@@ -359,6 +375,9 @@ def main():
         'roofline_encoder': {'kernel': 'scatter_kernel<ChannelsOp> (events_to_channels, %.0e events, %dx%d)' % (n_big, h, w),
                              'bound': 'hbm', 'achieved': enc_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': enc_gbs / hbm,
                              'traffic': None, 'mevents_per_s': n_big / (enc_ms * 1e-3) / 1e6},
+        'roofline_voxel': {'kernel': 'scatter_kernel<VoxelOp> (events_to_voxel, 5 bins, %.0e events, %dx%d)' % (n_vox, h, w),
+                           'bound': 'hbm', 'achieved': vox_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': vox_gbs / hbm,
+                           'traffic': None, 'mevents_per_s': n_vox / (vox_ms * 1e-3) / 1e6},
         'model_gflop_per_frame': FLOP_PER_PX[model_kind] * h * w / 1e9,
         'model_tflops': FLOP_PER_PX[model_kind] * h * w * value / 1e12,
         'cpu_baseline': {'value': cpu_fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',

@@ -950,13 +950,16 @@ extern "C" BMC_EXPORT int bmc_model_forward(bmc_model_t* m, const float* x, cons
     int rc = check_ready(m);
     if (rc) return rc;
     const bool full = m->kind == BMC_MODEL_BMCNET;
-    BMC_REQUIRE(x && x_h && x_o && out_h && out_o, "forward: NULL tensor");
-    BMC_REQUIRE(!full || (x_h_p && x_h_n && out_h_p && out_h_n), "forward: BMCNet needs x_h_p / x_h_n");
+    BMC_REQUIRE(x && out_h && out_o, "forward: NULL tensor");
+    BMC_REQUIRE(!full || (out_h_p && out_h_n), "forward: BMCNet needs out_h_p / out_h_n");
+    BMC_REQUIRE(!full || ((x_h != nullptr) == (x_h_p != nullptr) && (x_h != nullptr) == (x_h_n != nullptr)),
+                "forward: pass all hidden states or none");
+    BMC_REQUIRE(x_o || !init, "forward: x_o may only be omitted when init == 0 (fed-back prediction kept on the device)");
     cudaStream_t st = as_stream(stream);
     const float* hin[3] = {x_h, x_h_p, x_h_n};
     float* hout[3] = {out_h, out_h_p, out_h_n};
     const int nh = full ? 3 : 1;
-    for (int i = 0; i < nh; ++i) {
+    for (int i = 0; i < nh && x_h; ++i) {          // x_h == NULL: the states of the previous call are still resident
         rc = launch_pack_nchw(hin[i], m->g, 128, m->slot_ptr(m->slot_h[i]), 128, 0, st);
         if (rc) return rc;
     }

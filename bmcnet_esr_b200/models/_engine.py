@@ -25,6 +25,7 @@ class Engine:
         self.shape = None
         self.param_sig = None
         self.debug_simt = False
+        self._last = None          # the tensors returned by the previous forward() (and their versions)
 
     # -- lifetime -------------------------------------------------------------------------
     def _ensure_handle(self):
@@ -128,6 +129,7 @@ class Engine:
         x = x if x.dtype == torch.float32 else x.float()
         self.prepare(module, x)
         b, _, _, h, w = x.shape
+        x_o_in = x_o
         hs = [t.contiguous().float() for t in hiddens]
         x_o = x_o.contiguous().float()
         want = (b, 32, h, w) if init else (b, 2, 4 * h, 4 * w)
@@ -139,11 +141,19 @@ class Engine:
         outs = [torch.empty_like(t) for t in hs]
         out_o = torch.empty(b, 2, 4 * h, 4 * w, dtype=torch.float32, device=x.device)
         p = lambda t: C.c_void_p(t.data_ptr())
-        hp = [p(t) for t in hs] + [None] * (3 - len(hs))
+        # The reference loop feeds every call the previous call's outputs (infer_BMCNet.py:61-64).  When the
+        # arguments ARE those tensors, untouched, the states are still resident on the device: skip re-packing.
+        given = list(hiddens) + [x_o_in]
+        resident = (not init) and self._last is not None and self._last[0] == (self.shape, self.param_sig) and \
+            len(given) == len(self._last[1]) and all(a is b and a._version == v for a, (b, v) in zip(given, self._last[1]))
+        hp = [None] * 3 if resident else [p(t) for t in hs] + [None] * (3 - len(hs))
         op = [p(t) for t in outs] + [None] * (3 - len(outs))
         with torch.cuda.device(self.device):
-            check(lib().bmc_model_forward(self.handle, p(x), self._strides(x), hp[0], hp[1], hp[2], p(x_o),
-                                          int(bool(init)), op[0], op[1], op[2], p(out_o), stream_ptr()))
+            check(lib().bmc_model_forward(self.handle, p(x), self._strides(x), hp[0], hp[1], hp[2],
+                                          None if resident else p(x_o), int(bool(init)), op[0], op[1], op[2], p(out_o),
+                                          stream_ptr()))
+        # strong references: the memory cannot be recycled for another tensor while we compare by identity
+        self._last = ((self.shape, self.param_sig), [(t, t._version) for t in outs + [out_o]])
         return outs, out_o
 
     def step(self, module, x, reset, want_output=True):
@@ -152,6 +162,7 @@ class Engine:
         self.prepare(module, x)
         b, _, _, h, w = x.shape
         out_o = torch.empty(b, 2, 4 * h, 4 * w, dtype=torch.float32, device=x.device) if want_output else None
+        self._last = None
         with torch.cuda.device(self.device):
             check(lib().bmc_model_step(self.handle, C.c_void_p(x.data_ptr()), self._strides(x), int(bool(reset)),
                                        C.c_void_p(out_o.data_ptr()) if want_output else None, stream_ptr()))

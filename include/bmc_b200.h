@@ -138,7 +138,11 @@ int bmc_model_bind_workspace(bmc_model_t* m, void* workspace, size_t workspace_b
  *   out_*    device float32 outputs, same shapes as the inputs; out_o is [B,2,4H,4W].
  * Argument order and meaning follow BMCNet.forward (BMCNet.py:95) / BMCNet_plain.forward
  * (BMCNet_plain.py:44), including the positional hand-over of the three hidden states into
- * Backbone.forward (BMCNet.py:57 vs :115). */
+ * Backbone.forward (BMCNet.py:57 vs :115).
+ * Fast path for the recurrent loop of infer_BMCNet.py:46-68, where every call is fed the previous
+ * call's outputs: x_h (and x_h_p, x_h_n) may be NULL, meaning "the hidden states this model produced
+ * last are the inputs" (they are still resident in the workspace), and x_o may be NULL when init == 0,
+ * meaning "the previous prediction".  The mirror modules do this when they recognise their own outputs. */
 int bmc_model_forward(bmc_model_t* m, const float* x, const int64_t x_strides[5],
                       const float* x_h, const float* x_h_p, const float* x_h_n, const float* x_o,
                       int init, float* out_h, float* out_h_p, float* out_h_n, float* out_o,

@@ -176,3 +176,32 @@ def test_simt_cross_check_path_agrees(plain_ckpt):
     m._engine.set_debug_simt(False)
     assert (a[1] - b[1]).abs().max().item() <= 2e-3
     assert (a[0] - b[0]).abs().max().item() <= 2e-3 * a[0].abs().max().item() + 1e-3
+
+
+def test_resident_state_fast_path_equals_repacking(plain_ckpt):
+    """forward() skips re-packing the recurrent state when it is handed back its own, untouched outputs
+    (the loop of infer_BMCNet.py:61-64); clones of the same values must give bit-identical results."""
+    BMCNet, BMCNet_plain = _models()
+    for cls, sd, n_state in ((BMCNet_plain, plain_ckpt, 2),
+                             (BMCNet, O.surrogate_state_dict(plain=False, seed=5, transplant=plain_ckpt), 4)):
+        m = cls(4, 128, 5)
+        m.load_state_dict(sd, strict=True)
+        m = m.cuda().eval()
+        b, h, w = 2, 20, 33
+        xs = [synth_counts(b, h, w, 300 + s).cuda() for s in range(4)]
+        z = [torch.zeros(b, 128, h, w).cuda() for _ in range(n_state - 1)] + [torch.zeros(b, 32, h, w).cuda()]
+        st, fast = list(z), []
+        for s, x in enumerate(xs):
+            st = list(m(x, *st, s == 0))                      # own outputs handed straight back
+            fast.append([t.clone() for t in st])
+        st = list(z)
+        for s, x in enumerate(xs):
+            st = list(m(x, *[t.clone() for t in st], s == 0))  # same values in new tensors: full re-pack
+            for a, r in zip(st, fast[s]):
+                assert torch.equal(a, r), (cls.__name__, s)
+        # an in-place edit of a returned tensor must be seen (version bump -> re-pack)
+        st = list(m(xs[0], *z, True))
+        st[0].mul_(0.5)
+        a = m(xs[1], *st, False)
+        bb = m(xs[1], *[t.clone() for t in st], False)
+        assert torch.equal(a[-1], bb[-1]) and not torch.equal(a[-1], fast[1][-1])
