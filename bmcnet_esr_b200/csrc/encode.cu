@@ -94,6 +94,7 @@ struct Common {
     __device__ __forceinline__ bool quirks() const { return !(flags & BMC_ENC_NO_QUIRKS); }
     __device__ __forceinline__ int origin() const { return flip() ? (H - 1) * W : 0; }
     __device__ __forceinline__ void prepare(long) {}
+    __device__ __forceinline__ void group(long, int) {}      // called once per run of consecutive events
 };
 
 // events_to_channels (encodings.py:290-305)
@@ -172,6 +173,26 @@ struct VoxelOp : Common {
             h.add_float(b * H * W + pix, __fmul_rn(p, w));
         }
     }
+    // Pair form: the (at most) two non-zero weights of an event fall on ADJACENT bins j, j+1 with
+    // j = clamp(floor(tn), 0, bins-2), so both are delivered by one 64-bit update of a float2 slot
+    // (same weights as run(): every other bin's max(0, 1-|tn-b|) is zero).  Returns false when the
+    // event contributes nothing.
+    __device__ __forceinline__ bool pair(long i, float x, float y, float t, float p, int& slot,
+                                         float& lo, float& hi) const {
+        Pix q = decode_xy(x, y, H, W, flip());
+        const float fb = (float)(bins - 1);
+        float tn;
+        if (flags & BMC_ENC_TNORM) tn = __fmul_rn(__fdiv_rn(__fsub_rn(t, t0), dt), fb);
+        else tn = __fmul_rn(t, fb);
+        if (q.oor && mutate()) { xs[i] = 0.f; ys[i] = 0.f; }
+        if (q.oor && !quirks()) return false;
+        const int j = min(max((int)floorf(tn), 0), bins - 2);
+        lo = __fmul_rn(p, fmaxf(0.f, __fsub_rn(1.f, fabsf(__fsub_rn(tn, (float)j)))));
+        hi = __fmul_rn(p, fmaxf(0.f, __fsub_rn(1.f, fabsf(__fsub_rn(tn, (float)(j + 1))))));
+        if (q.oor && j == 0) lo = 0.f;      // bin 0 is the pass that drops out-of-range events
+        slot = j * H * W + (q.oor ? origin() : q.y * W + q.x);
+        return (lo != 0.f) | (hi != 0.f);
+    }
 };
 
 // events_to_stack_polarity / _no_polarity / voxel_torch(temporal_bilinear=False)
@@ -180,11 +201,18 @@ struct StackOp : Common {
     static constexpr bool kFloat = false, kNeedT = false, kSigned = true, kBounds = true;
     const long* beg; const long* end;    // device [bins]; re-pointed at a smem copy by the kernel
     int polarity;
+    unsigned long long live;             // bins whose range meets the current group of events
+    __device__ __forceinline__ void group(long i, int len) {
+        live = 0ull;
+        for (int b = 0; b < bins; ++b)
+            if (beg[b] < i + len && end[b] > i) live |= 1ull << b;
+    }
     template <class HT>
     __device__ __forceinline__ void run(HT& h, long i, float x, float y, float, float p) const {
         Pix q = decode_xy(x, y, H, W, false);
         bool first = true;
-        for (int b = 0; b < bins; ++b) {
+        for (unsigned long long m = live; m; m &= m - 1) {
+            const int b = __ffsll((long long)m) - 1;
             if (i < beg[b] || i >= end[b]) continue;
             const int plane = H * W;
             if (polarity) {
@@ -205,7 +233,7 @@ struct StackOp : Common {
 };
 
 // ---------------------------------------------------------------- the streaming kernel
-template <class Op, int MODE>
+template <class Op, int MODE, int kThreads>
 __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nbins, int* g_cnt,
                                                            float* g_ext, int vec_ok) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -228,22 +256,39 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nb
     op.prepare(n);
     __syncthreads();
 
+    // two 4-event groups per thread and iteration: all their loads are issued before the first
+    // atomic, which is what keeps enough bytes in flight when only one CTA fits an SM
     const long n4 = vec_ok ? (n >> 2) : 0;
     const long stride = (long)gridDim.x * kThreads;
-    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < n4; g += stride) {
-        const long i = g << 2;
+    for (long g = (long)blockIdx.x * kThreads + threadIdx.x; g < n4; g += 2 * stride) {
+        const long i = g << 2, i2 = (g + stride) << 2;
+        const bool two = g + stride < n4;
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 x = ldg_stream4(op.xs + i);
         const float4 y = ldg_stream4(op.ys + i);
         const float4 p = ldg_stream4(op.ps + i);
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (Op::kNeedT) t = ldg_stream4(op.ts + i);
+        const float4 t = Op::kNeedT ? ldg_stream4(op.ts + i) : z;
+        const float4 x2 = two ? ldg_stream4(op.xs + i2) : z;
+        const float4 y2 = two ? ldg_stream4(op.ys + i2) : z;
+        const float4 p2 = two ? ldg_stream4(op.ps + i2) : z;
+        const float4 t2 = (Op::kNeedT && two) ? ldg_stream4(op.ts + i2) : z;
+        op.group(i, 4);
         op.run(h, i + 0, x.x, y.x, t.x, p.x);
         op.run(h, i + 1, x.y, y.y, t.y, p.y);
         op.run(h, i + 2, x.z, y.z, t.z, p.z);
         op.run(h, i + 3, x.w, y.w, t.w, p.w);
+        if (two) {
+            op.group(i2, 4);
+            op.run(h, i2 + 0, x2.x, y2.x, t2.x, p2.x);
+            op.run(h, i2 + 1, x2.y, y2.y, t2.y, p2.y);
+            op.run(h, i2 + 2, x2.z, y2.z, t2.z, p2.z);
+            op.run(h, i2 + 3, x2.w, y2.w, t2.w, p2.w);
+        }
     }
-    for (long i = (n4 << 2) + (long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride)
+    for (long i = (n4 << 2) + (long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        op.group(i, 1);
         op.run(h, i, op.xs[i], op.ys[i], Op::kNeedT ? op.ts[i] : 0.f, op.ps[i]);
+    }
 
     if (MODE == kGlobal) return;
     __syncthreads();
@@ -259,6 +304,60 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nb
             if (v >> 16) atomicAdd(&g_cnt[2 * k + 1], (int)(v >> 16));
         }
     }
+}
+
+// Time-interpolated voxels on grids too large for shared memory, pair form (events_to_voxel /
+// events_to_voxel_torch bilinear).  Global fp32 reductions run in the L2 atomic units (~140 G
+// reductions/s on spread addresses, measured); `red.global.add.v2.f32` updates BOTH adjacent
+// bins of an event with one 8-byte reduction when the grid is laid out as float2 slots
+// [bins-1][H*W] (.x -> bin j, .y -> bin j+1): one reduction per event instead of two
+// (180x320x5: 74 -> 140 Gevents/s).  Each CTA streams a CONTIGUOUS range of events: with
+// time-sorted input the CTAs then work on different bins at any moment, which spreads the
+// reductions over the whole grid.  finalize_pairs_kernel folds the slots into [bins][H][W].
+// (Grids that fit shared memory stay on scatter_kernel: the shared and the L2 atomic paths share
+// the SM's load/store issue, so splitting events between them only lowered the rate -- DESIGN.md.)
+constexpr int kPairThreads = 512;
+
+__device__ __forceinline__ void red_global_f32x2(float2* addr, float lo, float hi) {
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(lo), "f"(hi) : "memory");
+}
+
+__global__ void __launch_bounds__(kPairThreads) voxel_pair_kernel(VoxelOp op, long n, float2* g_pairs,
+                                                                   int vec_ok) {
+    op.prepare(n);
+    auto add = [&](long i, float x, float y, float t, float p) {
+        int slot; float lo, hi;
+        if (op.pair(i, x, y, t, p, slot, lo, hi)) red_global_f32x2(&g_pairs[slot], lo, hi);
+    };
+    const long n4 = vec_ok ? (n >> 2) : 0;
+    const long per_cta = (n4 + gridDim.x - 1) / gridDim.x;
+    const long g_end = min(n4, (long)(blockIdx.x + 1) * per_cta);
+    for (long g = (long)blockIdx.x * per_cta + threadIdx.x; g < g_end; g += kPairThreads) {
+        const long i = g << 2;
+        const float4 x = ldg_stream4(op.xs + i);
+        const float4 y = ldg_stream4(op.ys + i);
+        const float4 p = ldg_stream4(op.ps + i);
+        const float4 t = ldg_stream4(op.ts + i);
+        add(i + 0, x.x, y.x, t.x, p.x);
+        add(i + 1, x.y, y.y, t.y, p.y);
+        add(i + 2, x.z, y.z, t.z, p.z);
+        add(i + 3, x.w, y.w, t.w, p.w);
+    }
+    const long stride = (long)gridDim.x * kPairThreads;
+    for (long i = (n4 << 2) + (long)blockIdx.x * kPairThreads + threadIdx.x; i < n; i += stride)
+        add(i, op.xs[i], op.ys[i], op.ts[i], op.ps[i]);
+}
+
+// out[b][pix] = pairs[b][pix].x + pairs[b-1][pix].y
+__global__ void finalize_pairs_kernel(const float2* __restrict__ pairs, float* __restrict__ out,
+                                      int bins, int plane) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)bins * plane) return;
+    const int b = (int)(i / plane);
+    float v = 0.f;
+    if (b < bins - 1) v = pairs[i].x;
+    if (b > 0) v = __fadd_rn(v, pairs[i - plane].y);
+    out[i] = v;
 }
 
 // out = fp32(saturated count) + fp32 extras; the reference's serial `+= 1.0f` sticks at 2^24.
@@ -350,28 +449,34 @@ int carve(void* ws, size_t ws_bytes_given, long out_elems, Ws& w) {
     return BMC_OK;
 }
 
-template <class Op, int MODE>
-int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaStream_t st) {
-    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : 0);
-    auto kern = scatter_kernel<Op, MODE>;
+template <class Op, int MODE, int THREADS>
+int launch_threads(const Op& op, long n, int nbins, const Ws& w, int vec_ok, size_t smem, int per_sm,
+                   cudaStream_t st) {
+    auto kern = scatter_kernel<Op, MODE, THREADS>;
     if (smem > 48 * 1024)
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    BMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kThreads, smem));
-    if (per_sm < 1) per_sm = 1;
-    if (per_sm > 4) per_sm = 4;
     // Persistent grid: a multiple of the SM count, but never so many CTAs that flushing
     // `nbins` bins per CTA outweighs the events each CTA streams.
-    long want = (n + (long)kThreads * 4 * 8 - 1) / ((long)kThreads * 4 * 8);
+    long want = (n + (long)THREADS * 4 * 8 - 1) / ((long)THREADS * 4 * 8);
     if (MODE != kGlobal) {
         long by_flush = n / (4L * nbins) + 1;
         if (want > by_flush) want = by_flush;
     }
     long grid = (long)sm_count() * per_sm;
     if (want < grid) grid = want < 1 ? 1 : want;
-    kern<<<(unsigned)grid, kThreads, smem, st>>>(op, n, nbins, w.cnt, w.ext, vec_ok);
+    kern<<<(unsigned)grid, THREADS, smem, st>>>(op, n, nbins, w.cnt, w.ext, vec_ok);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
+}
+
+template <class Op, int MODE>
+int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaStream_t st) {
+    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : 0);
+    int per_sm = 1;
+    BMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scatter_kernel<Op, MODE, kThreads>, kThreads, smem));
+    // a grid that leaves room for one CTA per SM only gets 1024 threads to keep loads in flight
+    if (per_sm < 2) return launch_threads<Op, MODE, 1024>(op, n, nbins, w, vec_ok, smem, 1, st);
+    return launch_threads<Op, MODE, kThreads>(op, n, nbins, w, vec_ok, smem, per_sm > 4 ? 4 : per_sm, st);
 }
 
 template <class Op>
@@ -393,6 +498,29 @@ int run_scatter(const Op& op, long n, long out_elems, float* out, void* ws, size
     }
     const int thr = 256;
     finalize_kernel<<<(unsigned)((out_elems + thr - 1) / thr), thr, 0, st>>>(w.cnt, w.ext, out, out_elems);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int run_voxel_pairs(const VoxelOp& op, long n, float* out, void* ws, size_t wsb, cudaStream_t st) {
+    const int plane = op.H * op.W;
+    const long out_elems = (long)op.bins * plane;
+    Ws w;
+    int rc = carve(ws, wsb, out_elems, w);
+    if (rc) return rc;
+    // the float2 slot grid [bins-1][plane] overlays the cnt + ext areas (2*bins*plane words)
+    float2* pairs = reinterpret_cast<float2*>(w.cnt);
+    BMC_CUDA(cudaMemsetAsync(pairs, 0, (size_t)(op.bins - 1) * plane * 8, st));
+    if (n > 0) {
+        const int vec_ok = (((uintptr_t)op.xs | (uintptr_t)op.ys | (uintptr_t)op.ps | (uintptr_t)op.ts) & 15) == 0;
+        long grid = (long)sm_count() * 4;
+        const long want = (n + (long)kPairThreads * 4 * 8 - 1) / ((long)kPairThreads * 4 * 8);
+        if (grid > want) grid = want < 1 ? 1 : want;
+        voxel_pair_kernel<<<(unsigned)grid, kPairThreads, 0, st>>>(op, n, pairs, vec_ok);
+        BMC_CUDA(cudaGetLastError());
+    }
+    const int thr = 256;
+    finalize_pairs_kernel<<<(unsigned)((out_elems + thr - 1) / thr), thr, 0, st>>>(pairs, out, op.bins, plane);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
@@ -464,6 +592,8 @@ extern "C" BMC_EXPORT int bmc_encode_voxel(float* xs, float* ys, const float* ts
     op.xs = xs; op.ys = ys; op.ts = ts; op.ps = const_cast<float*>(ps);
     op.H = H; op.W = W; op.bins = bins; op.flags = flags;
     op.t0 = 0.f; op.dt = 1.f;     // BMC_ENC_TNORM: filled in on the device (VoxelOp::prepare)
+    if (bins >= 2 && (long)bins * H * W > kMaxBinsSmem32)      // too large for shared-memory bins
+        return run_voxel_pairs(op, n, out, workspace, workspace_bytes, as_stream(stream));
     return run_scatter(op, n, (long)bins * H * W, out, workspace, workspace_bytes, as_stream(stream));
 }
 

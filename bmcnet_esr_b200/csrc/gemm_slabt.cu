@@ -332,7 +332,12 @@ int launch_conv_slabt(GemmParams p, cudaStream_t st) {
         BMC_CUDA(cudaFuncSetAttribute(conv_slabt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
-    const int grid = p.n_full < sm_count() ? p.n_full : sm_count();
+    int grid = p.n_full < sm_count() ? p.n_full : sm_count();
+    {   // measurement switch: fewer CTAs -> is a tile's time set by the SM or by the shared L2 fabric?
+        static int cap = -1;
+        if (cap < 0) { const char* e = getenv("BMC_SLABT_GRID"); cap = e ? atoi(e) : 0; }
+        if (cap > 0 && grid > cap) grid = cap;
+    }
     conv_slabt_tc<<<grid, kThreadsT, smem, st>>>(p);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;

@@ -150,9 +150,14 @@ def binary_search_torch_tensor(t, l, r, x, side='left'):
 
 def _early_out(ts, B, sensor_size, device):
     # reference encodings.py:122-123,166-167,217-218: [B,H,W] zeros, also for the polarity stack
-    if len(ts) <= 3 or bool((ts == 0).all()):
-        return torch.zeros([B, sensor_size[0], sensor_size[1]], device=device)
-    return None
+    # (`ts.sum() == 0` there; for the sorted, normalised ts >= 0 of base_dataset.py:30 that is "all
+    # zero".)  The return SHAPE depends on it, so the host has to know: read the two end samples
+    # first (8 bytes) and scan the whole array only when both are zero.
+    if len(ts) > 3:
+        first, last = ts[[0, -1]].tolist()
+        if first != 0 or last != 0 or not bool((ts == 0).all()):
+            return None
+    return torch.zeros([B, sensor_size[0], sensor_size[1]], device=device)
 
 
 def _stack(xs, ys, ts, ps, B, device, sensor_size, polarity):
