@@ -228,6 +228,10 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr, uin
 __host__ __device__ constexpr uint32_t umma_desc_hi_sw128(uint32_t sbo_bytes) {
     return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
 }
+// K-major rows of 64 bytes under SWIZZLE_64B (layout code 4): 8-row groups are `sbo_bytes` = 512 apart
+__host__ __device__ constexpr uint32_t umma_desc_hi_sw64(uint32_t sbo_bytes) {
+    return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (4u << 29);
+}
 __device__ __forceinline__ uint32_t umma_desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
     return ((smem_addr >> 4) & 0x3FFF) | (((lbo_bytes >> 4) & 0x3FFF) << 16);
 }
@@ -341,5 +345,7 @@ __device__ __forceinline__ float from_act(act_t a) { return __half2float(a); }
 // 2-D act_t row-major [rows][cols] tensor, box = [box_rows][box_cols], 128-byte swizzle.
 int make_tmap_2d_act(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols,
                       uint32_t box_rows, uint32_t box_cols);
+// Same tensor, box = [box_rows][32], 64-byte swizzle (box_rows a multiple of 8).
+int make_tmap_2d_act_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
 
 }  // namespace bmc

@@ -19,6 +19,7 @@ namespace bmc {
 constexpr int kMaxSeg = 4;
 constexpr int kMaxJobs = 8;
 constexpr int kMaxMaps = 8;
+constexpr int kMaxMaps32 = 6;
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
 
@@ -56,6 +57,9 @@ struct GemmJobDev {
     int t1_map[kMaxSeg];       // TMA map of the segment's weights [.][64], chunk-major [chunks][128][64]
     int t1_row[kMaxSeg], t1_img_stride[kMaxSeg];
     const float* bias_img;     // per-image extra bias [B][128] added to `bias`, or NULL
+    // conv_slab2_tc (gemm_slab2.cu): the same operands behind 32-channel / 64-byte-swizzle boxes,
+    // indices into GemmParams::maps32 (valid when GemmParams::has32)
+    signed char a_map32[kMaxSeg], t1_map32[kMaxSeg], w_map32;
 };
 
 struct alignas(64) GemmParams {
@@ -80,9 +84,20 @@ struct alignas(64) GemmParams {
     int n_full, n_half, full_per_img;
     int pairs_per_job;         // pair kernel (gemm_pair.cu): 512-row pair tiles per job
     long long* prof;           // optional per-CTA cycle counters (tools/gpu_diag.py slabprof), else NULL
+    // conv_slab2_tc: 32-channel boxes (activations: abox32_rows x 32, weights: 128 x 32), 64-byte swizzle
+    CUtensorMap maps32[kMaxMaps32];
+    int has32, abox32_rows, slab2_stages;
+    // its K steps (segment x 32 channels), built by the launcher
+    struct {
+        int n;                             // steps per tile (even)
+        unsigned t1, pm;                   // per step: centre tap only / per-image weights
+        unsigned char seg[16], c64[16], cs[16];     // segment, 64-channel chunk inside it, chunks of the segment
+        short col[16], kchunk0[16];        // first channel inside the segment; first K chunk of the weight matrix
+    } s2;
 };
 
-static_assert(sizeof(GemmParams) <= 4096, "GemmParams must fit the classic 4 KB kernel parameter space");
+// > 4 KB of kernel parameters needs CUDA >= 12.1 on sm_70+ (limit 32764 bytes); sm_100a only here
+static_assert(sizeof(GemmParams) <= 8192, "GemmParams grew unexpectedly");
 
 // att[b] = centres[b]^T . v[b] (split over pixel ranges) -- submodules.py:69-70
 constexpr int kMaxPairs = 4;
@@ -151,6 +166,9 @@ int slab_box_rows(const Geom& g, int n_taps);   // TMA box height the slab kerne
 bool pair_supported(const GemmParams& p);
 bool slabt_supported(const GemmParams& p);
 int launch_conv_slabt(GemmParams p, cudaStream_t st);
+bool slab2_supported(const GemmParams& p);
+int slab2_box_rows(const Geom& g, int n_taps);   // TMA box height conv_slab2_tc expects behind the activation maps32
+int launch_conv_slab2(GemmParams p, cudaStream_t st);
 int launch_conv_pair(GemmParams p, cudaStream_t st);
 int launch_conv_slab(GemmParams p, cudaStream_t st);
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st);

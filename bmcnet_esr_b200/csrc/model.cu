@@ -168,7 +168,9 @@ struct bmc_model {
     bool allow_fused = true;
     char* ws = nullptr;
     CUtensorMap map_act, map_att, map_slab, map_mi, map_mi64, map_w128, map_w64, map_w32, map_p;
+    CUtensorMap map_act_s64, map_mi_s64, map_w_s64, map_p_s64;   // 32-channel / 64-byte-swizzle boxes (conv_slab2_tc)
     int abox = 64;                         // rows per TMA box of map_slab / map_mi64 (slab_box_rows)
+    int abox32 = 64;                       // rows per TMA box of map_act_s64 / map_mi_s64 (slab2_box_rows)
     // plan
     std::vector<Op> ops;
     std::vector<int> free_slots;
@@ -308,6 +310,8 @@ struct Builder {
         p.maps[5] = m->map_mi64;
         p.maps[6] = m->map_w64;
         p.maps[7] = m->map_att;                 // act arena, 64-row boxes (1x1 launches of the unfused plan)
+        p.maps32[0] = m->map_act_s64; p.maps32[1] = m->map_mi_s64; p.maps32[2] = m->map_w_s64; p.maps32[3] = m->map_p_s64;
+        p.has32 = taps == 9; p.abox32_rows = m->abox32;
         p.n_jobs = (int)jobs.size();
         const int n_plain = (int)jobs[0].segs.size();
         p.n_seg = n_plain + (jobs[0].mix_slot >= 0) + (jobs[0].ident_slot >= 0);
@@ -323,31 +327,31 @@ struct Builder {
                 const int sg = (int)segs.size();
                 segs.push_back({0, js.mix_slot});
                 p.tap1_mask |= 1 << sg;
-                d.t1_map[sg] = 3; d.t1_row[sg] = js.mix_pair * g.B * 256; d.t1_img_stride[sg] = 256;
+                d.t1_map[sg] = 3; d.t1_map32[sg] = 3; d.t1_row[sg] = js.mix_pair * g.B * 256; d.t1_img_stride[sg] = 256;
                 d.bias_img = m->bimg_ptr() + (size_t)js.mix_pair * g.B * 128;
             }
             if (js.ident_slot >= 0) {
                 const int sg = (int)segs.size();
                 segs.push_back({0, js.ident_slot});
                 p.tap1_mask |= 1 << sg;
-                d.t1_map[sg] = 2; d.t1_row[sg] = m->ident_row; d.t1_img_stride[sg] = 0;
+                d.t1_map[sg] = 2; d.t1_map32[sg] = 2; d.t1_row[sg] = m->ident_row; d.t1_img_stride[sg] = 0;
             }
             for (int s = 0; s < p.n_seg; ++s) {
                 const Src& src = segs[s];
                 if (src.kind == 1) {
-                    d.a_map[s] = 1; d.a_map64[s] = 5; d.a_row_base[s] = 0; d.a_ptr[s] = m->mi_ptr(); d.a_ld[s] = 64; d.a_rows[s] = g.rows();
+                    d.a_map[s] = 1; d.a_map64[s] = 5; d.a_map32[s] = 1; d.a_row_base[s] = 0; d.a_ptr[s] = m->mi_ptr(); d.a_ld[s] = 64; d.a_rows[s] = g.rows();
                 } else {
-                    d.a_map[s] = 0; d.a_map64[s] = taps == 9 ? 4 : 7; d.a_row_base[s] = (int)(src.slot * g.rows());
+                    d.a_map[s] = 0; d.a_map64[s] = taps == 9 ? 4 : 7; d.a_map32[s] = 0; d.a_row_base[s] = (int)(src.slot * g.rows());
                     d.a_ptr[s] = m->slot_ptr(0); d.a_ld[s] = 128; d.a_rows[s] = (long)m->n_slots * g.rows();
                 }
                 d.a_col_base[s] = 0;
             }
             if (js.weight >= 0) {
                 const WeightSpec& w = m->weights[js.weight];
-                d.w_map = 2; d.w_map64 = n == 128 ? 6 : 0; d.w_ptr = m->w_dev; d.w_rows = w.n_out; d.w_row_base = w.row_base; d.w_img_stride = 0;
+                d.w_map = 2; d.w_map64 = n == 128 ? 6 : 0; d.w_map32 = 2; d.w_ptr = m->w_dev; d.w_rows = w.n_out; d.w_row_base = w.row_base; d.w_img_stride = 0;
                 d.bias = m->f32_dev + w.bias_off;
             } else {
-                d.w_map = 3; d.w_ptr = m->p_ptr(); d.w_rows = 128;
+                d.w_map = 3; d.w_map32 = -1; d.w_ptr = m->p_ptr(); d.w_rows = 128;
                 d.w_row_base = js.dyn_pair * g.B * 256; d.w_img_stride = 256; d.bias = nullptr;
             }
             d.relu = js.relu ? 1 : 0;
@@ -829,6 +833,8 @@ extern "C" BMC_EXPORT int bmc_model_load_state_dict(bmc_model_t* m, const char* 
     if (rc) return rc;
     rc = make_tmap_2d_act(&m->map_w32, m->w_dev, (uint64_t)m->w_rows_total, 64, 32, 64);
     if (rc) return rc;
+    rc = make_tmap_2d_act_sw64(&m->map_w_s64, m->w_dev, (uint64_t)m->w_rows_total, 64, 128);
+    if (rc) return rc;
     m->loaded = true;
     if (m->bound) {            // weights moved: rebuild the plan against the new pointers
         drop_graph(m);
@@ -911,6 +917,10 @@ extern "C" BMC_EXPORT int bmc_model_bind_workspace(bmc_model_t* m, void* workspa
     if (!rc) rc = make_tmap_2d_act(&m->map_mi, m->mi_ptr(), rows, 64, 128, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_mi64, m->mi_ptr(), rows, 64, (uint32_t)m->abox, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_p, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128, 64);
+    m->abox32 = slab2_box_rows(m->g, 9);
+    if (!rc) rc = make_tmap_2d_act_sw64(&m->map_act_s64, m->slot_ptr(0), rows * m->n_slots, 128, (uint32_t)m->abox32);
+    if (!rc) rc = make_tmap_2d_act_sw64(&m->map_mi_s64, m->mi_ptr(), rows, 64, (uint32_t)m->abox32);
+    if (!rc) rc = make_tmap_2d_act_sw64(&m->map_p_s64, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128);
     if (rc) return rc;
     m->dry = false;
     Builder b{m};
@@ -1074,6 +1084,39 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
     if (!maps64_ok)
         for (int j = 0; j < n_jobs; ++j)
             for (int s = 0; s < kMaxSeg; ++s) p.jobs[j].a_map64[s] = -1;
+    // 32-channel / 64-byte-swizzle boxes for conv_slab2_tc, if the distinct tensors fit
+    if (impl == 0 && n == 128) {
+        int n32 = 0;
+        std::vector<std::pair<const void*, uint32_t>> key32;
+        bool ok = true;
+        auto get32 = [&](const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows, signed char* idx) -> int {
+            for (size_t i = 0; i < key32.size(); ++i)
+                if (key32[i].first == ptr && key32[i].second == box_rows) { *idx = (signed char)i; return BMC_OK; }
+            if (n32 >= kMaxMaps32) { *idx = -1; ok = false; return BMC_OK; }
+            int rc = make_tmap_2d_act_sw64(&p.maps32[n32], ptr, rows, cols, box_rows);
+            if (rc) return rc;
+            key32.push_back({ptr, box_rows});
+            *idx = (signed char)n32++;
+            return BMC_OK;
+        };
+        p.abox32_rows = slab2_box_rows(g, taps);
+        for (int j = 0; j < n_jobs && ok; ++j) {
+            GemmJobDev& d = p.jobs[j];
+            for (int s = 0; s < p.n_seg && ok; ++s) {
+                int rc = get32(jobs[j].a[s], (uint64_t)jobs[j].a_rows[s], (uint64_t)jobs[j].a_ch[s], (uint32_t)p.abox32_rows, &d.a_map32[s]);
+                if (rc) return rc;
+            }
+            if (ok && jobs[j].w_img_stride == 0) {
+                int kch = 0;
+                for (int s = 0; s < p.n_seg; ++s) kch += p.chunks[s] * taps;
+                int rc = get32(jobs[j].w, (uint64_t)jobs[j].w_row_base + (uint64_t)jobs[j].w_rows * kch, 64, 128, &d.w_map32);
+                if (rc) return rc;
+            } else {
+                d.w_map32 = -1;
+            }
+        }
+        p.has32 = ok ? 1 : 0;
+    }
     return launch_conv_gemm(p, impl, as_stream(stream));
 }
 

@@ -85,6 +85,34 @@ int make_tmap_2d_act(CUtensorMap* out, const void* base, uint64_t rows, uint64_t
     return BMC_OK;
 }
 
+// Same tensor behind 32-channel boxes (64-byte rows in shared memory, 64-byte swizzle): the operand
+// granule of conv_slab2_tc (gemm_slab2.cu).
+int make_tmap_2d_act_sw64(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+    encode_tiled_fn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+        return BMC_ERR_CUDA;
+    }
+    if (((uintptr_t)base & 15) || (cols * 2) % 16 || cols % 32 || box_rows > 256 || box_rows % 8) {
+        set_error("make_tmap_2d_act_sw64: bad alignment/box (base %p cols %llu box rows %u)", base,
+                  (unsigned long long)cols, box_rows);
+        return BMC_ERR_ARG;
+    }
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {32, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, kTmapType, 2, const_cast<void*>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (sw64) failed with CUresult %d (rows %llu cols %llu box rows %u)",
+                  (int)r, (unsigned long long)rows, (unsigned long long)cols, box_rows);
+        return BMC_ERR_CUDA;
+    }
+    return BMC_OK;
+}
+
 }  // namespace bmc
 
 extern "C" BMC_EXPORT int bmc_abi_version(void) { return BMC_ABI_VERSION; }

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for g in 148 111 74 37 16; do BMC_SLABT_GRID=$g timeout 120 python tools/time_conv.py 57 2 2>&1 | grep conv3x3 | tee -a gpurun_out/convgrid.txt; done

@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+for d in 0 1 2 3; do for g in 148 16; do BMC_SLAB2_DBG=$d BMC_CONV_SLAB2=1 BMC_SLABT_GRID=$g timeout 120 python tools/time_conv.py 57 2 2>&1 | grep -E "conv3x3|rror|slab2prof" | sed "s/^/dbg=$d /" | tee -a gpurun_out/slab2prof.txt; done; done
