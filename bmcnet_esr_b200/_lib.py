@@ -50,6 +50,7 @@ SIGNATURES = {
     'bmc_layernorm_rows': (_i, [_vp, _vp, _vp, _f, _i64, _vp, _vp]),
     'bmc_pack_nchw': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     'bmc_unpack_nchw': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'bmc_sr_metrics': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
 }
 
 _lib = None

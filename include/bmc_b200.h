@@ -217,6 +217,17 @@ int bmc_pack_nchw(const float* src, int B, int C, int H, int W, void* dst_act16,
 int bmc_unpack_nchw(const void* src_act16, int B, int C, int H, int W, int c_pad, int c_off,
                     float* dst, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Evaluation tail of the inference loop (reference infer_BMCNet.py:77-87), on the device:
+ *   sums[0] = sum((resize(pred) - gt)^2)   resize = bicubic to the gt size when the sizes differ (:78-79)
+ *   sums[1] = sum((bicubic(inp) - gt)^2)   the bicubic baseline of the LR count frame (:80)
+ * over all B*C*Hg*Wg ground-truth elements (nn.MSELoss divides by that count, :83-84).
+ * pred: device float [B,C,Hp,Wp]; inp: [B,C,H,W]; gt: [B,C,Hg,Wg], all contiguous;
+ * sums: device double[2], overwritten.  Nothing is copied to the host.
+ * ---------------------------------------------------------------------------------------- */
+int bmc_sr_metrics(const float* pred, int B, int C, int Hp, int Wp, const float* inp, int H, int W,
+                   const float* gt, int Hg, int Wg, double* sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
