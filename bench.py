@@ -13,8 +13,9 @@ each GPU: encode the step's two event windows per sequence into per-polarity cou
   e2e     through the reference-facing API (`model(x, h, o, init)` + `events_to_channels_windows`)
           with the step's events copied from pinned host memory and the prediction read back to
           the host inside the timed region, every step.
-  roofline  the dominant kernel (3x3 128->128 implicit-GEMM conv, tcgen05) timed live, back to
-          back, at this workload's shape; algorithmic FLOPs = 2*147456 MAC per real LR pixel.
+  roofline  the dominant kernel (3x3 128->128 implicit-GEMM conv, tcgen05: conv_slab2_tc) timed live,
+          back to back, at this workload's shape; algorithmic FLOPs = 2*147456 MAC per real LR pixel;
+          `traffic` = DRAM bytes per launch of the committed ncu --set full capture (profiles/).
   cpu_baseline / --impl reference  the CPU oracle (fp32 PyTorch restatement of the reference
           forward + numpy encoder) on the host cores, on a bounded sample (B=1 sequences).
 
@@ -42,6 +43,11 @@ WORKLOADS = {
                          'BMCNet x4, EventZoom LR 31x56 -> 124x224, surrogate weights (checkpoint not shipped)'),
 }
 CONV_MAC_PER_PX = 147456          # 3x3 128->128
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_ncu_full_*.txt):
+# conv_slab2_tc, 2 jobs, B=57, 45x80: 116.2 + 69.3 MB (algorithmic 115.8 read + 115.8 written; part of the output is
+# still dirty in L2 when the kernel ends); encoders: bytes per event at 1e8 events (12.04 / 16.04 for 12 / 16 algorithmic)
+NCU_CONV_TRAFFIC = {('plain', 57, 45, 80): 185.5e6}
+NCU_ENC_BYTES_PER_EVENT, NCU_VOX_BYTES_PER_EVENT = 12.045, 16.035
 FLOP_PER_PX = {'plain': 9721856, 'full': 41574912}      # SURVEY 8d / BASELINE.md section 3
 
 
@@ -348,8 +354,10 @@ def main():
     conv_flops = 2.0 * CONV_MAC_PER_PX * h * w * B * jobs
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12
     peak = peaks.get('bf16_tflops', 1590.0)
-    roofline = {'kernel': 'conv_slabt_tc (3x3 128->128 implicit GEMM, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
-                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak, 'traffic': None,
+    roofline = {'kernel': 'conv_slab2_tc (3x3 128->128 implicit GEMM, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
+                'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
+                'traffic': NCU_CONV_TRAFFIC.get((model_kind, B, h, w)), 'traffic_unit': 'bytes per launch (ncu, profiles/r01_ncu_full_slab2_plain3x3.txt)',
+                'algorithmic_bytes': 2.0 * jobs * B * 128 * 2 * ((h + 2) * (w + 2) + 127) // 128 * 128,
                 'us_per_launch': conv_ms * 1e3,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)'}
 
@@ -404,10 +412,12 @@ def main():
         'roofline': roofline,
         'roofline_encoder': {'kernel': 'scatter_kernel<ChannelsOp> (events_to_channels, %.0e events, %dx%d)' % (n_big, h, w),
                              'bound': 'hbm', 'achieved': enc_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': enc_gbs / hbm,
-                             'traffic': None, 'mevents_per_s': n_big / (enc_ms * 1e-3) / 1e6},
+                             'traffic': NCU_ENC_BYTES_PER_EVENT * n_big if (h, w) == (45, 80) else None,
+                             'mevents_per_s': n_big / (enc_ms * 1e-3) / 1e6},
         'roofline_voxel': {'kernel': 'scatter_kernel<VoxelOp> (events_to_voxel, 5 bins, %.0e events, %dx%d)' % (n_vox, h, w),
                            'bound': 'hbm', 'achieved': vox_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': vox_gbs / hbm,
-                           'traffic': None, 'mevents_per_s': n_vox / (vox_ms * 1e-3) / 1e6},
+                           'traffic': NCU_VOX_BYTES_PER_EVENT * n_vox if (h, w) == (45, 80) else None,
+                           'mevents_per_s': n_vox / (vox_ms * 1e-3) / 1e6},
         'model_gflop_per_frame': FLOP_PER_PX[model_kind] * h * w / 1e9,
         'model_tflops': FLOP_PER_PX[model_kind] * h * w * value / 1e12,
         'cpu_baseline': {'value': cpu_fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',

@@ -158,7 +158,8 @@ __device__ __forceinline__ void lerp_taps(int d, int n, int& i0, int& i1, float&
     i1 = i0 + (i0 < n - 1 ? 1 : 0);
     l1 = s - (float)i0;
 }
-__global__ void emit_output(EmitParams p) {
+__device__ __forceinline__ float sel3(int k, float a, float b, float c) { return k == 0 ? a : (k == 1 ? b : c); }
+__global__ void __launch_bounds__(128) emit_output(EmitParams p) {
     const Geom g = p.g;
     const int HW = g.H * g.W;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -167,25 +168,48 @@ __global__ void emit_output(EmitParams p) {
     const int pix = (int)(idx - (long)b * HW);
     const int y = pix / g.W, x = pix - y * g.W;
     const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
-    const float* a = p.a + row * 32;
     float o[32];
+    {
+        const float4* a4 = reinterpret_cast<const float4*>(p.a + row * 32);     // 128-byte aligned row
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float4 v = a4[i];
+            o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+        }
+    }
+    // the 4x4 outputs of an LR pixel interpolate inside its 3x3 neighbourhood of f2: 9 loads per plane;
+    // tap indices / weights exactly as lerp_taps gives them (same arithmetic as one load per tap)
+    int ky0[4], ky1[4], kx0[4], kx1[4];
+    float ly[4], lx[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        int i0, i1;
+        lerp_taps(4 * y + r, g.H, i0, i1, ly[r]); ky0[r] = i0 - (y - 1); ky1[r] = i1 - (y - 1);
+        lerp_taps(4 * x + r, g.W, i0, i1, lx[r]); kx0[r] = i0 - (x - 1); kx1[r] = i1 - (x - 1);
+    }
+    const int yc[3] = {max(y - 1, 0), y, min(y + 1, g.H - 1)}, xc[3] = {max(x - 1, 0), x, min(x + 1, g.W - 1)};
 #pragma unroll
     for (int c = 0; c < 2; ++c) {
         const float* f2 = p.x + b * p.xs[0] + c * p.xs[1] + p.xs[2];
+        float P[3][3];
 #pragma unroll
-        for (int ry = 0; ry < 4; ++ry) {
-            int y0, y1; float ly;
-            lerp_taps(4 * y + ry, g.H, y0, y1, ly);
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) P[k][l] = f2[yc[k] * p.xs[3] + xc[l] * p.xs[4]];
+        float Hx[3][4];                                    // x-interpolated rows
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int rx = 0; rx < 4; ++rx)
+                Hx[k][rx] = (1.f - lx[rx]) * sel3(kx0[rx], P[k][0], P[k][1], P[k][2]) + lx[rx] * sel3(kx1[rx], P[k][0], P[k][1], P[k][2]);
+#pragma unroll
+        for (int ry = 0; ry < 4; ++ry)
 #pragma unroll
             for (int rx = 0; rx < 4; ++rx) {
-                int x0, x1; float lx;
-                lerp_taps(4 * x + rx, g.W, x0, x1, lx);
-                const float v00 = f2[y0 * p.xs[3] + x0 * p.xs[4]], v01 = f2[y0 * p.xs[3] + x1 * p.xs[4]];
-                const float v10 = f2[y1 * p.xs[3] + x0 * p.xs[4]], v11 = f2[y1 * p.xs[3] + x1 * p.xs[4]];
-                const float up = (1.f - ly) * ((1.f - lx) * v00 + lx * v01) + ly * ((1.f - lx) * v10 + lx * v11);
-                o[c * 16 + ry * 4 + rx] = a[c * 16 + ry * 4 + rx] + up;
+                const float up = (1.f - ly[ry]) * sel3(ky0[ry], Hx[0][rx], Hx[1][rx], Hx[2][rx]) +
+                                 ly[ry] * sel3(ky1[ry], Hx[0][rx], Hx[1][rx], Hx[2][rx]);
+                o[c * 16 + ry * 4 + rx] += up;
             }
-        }
     }
     if (p.out_o) {
         const int W4 = 4 * g.W;
@@ -197,9 +221,9 @@ __global__ void emit_output(EmitParams p) {
                     make_float4(o[c * 16 + ry * 4], o[c * 16 + ry * 4 + 1], o[c * 16 + ry * 4 + 2], o[c * 16 + ry * 4 + 3]);
     }
     if (p.mi_next) {
-        uint32_t* dw = reinterpret_cast<uint32_t*>(p.mi_next + row * 64);
+        uint2* d2 = reinterpret_cast<uint2*>(p.mi_next + row * 64 + 12);        // channels 12..43: byte offset 24, 8-byte aligned
 #pragma unroll
-        for (int c = 0; c < 16; ++c) dw[6 + c] = pack_act2(o[2 * c], o[2 * c + 1]);
+        for (int c = 0; c < 8; ++c) d2[c] = make_uint2(pack_act2(o[4 * c], o[4 * c + 1]), pack_act2(o[4 * c + 2], o[4 * c + 3]));
     }
 }
 
