@@ -32,6 +32,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# rank 0 prints ONE JSON line on stdout; NCCL's version banner (NCCL_DEBUG=VERSION) would precede it
+if os.environ.get('NCCL_DEBUG', 'VERSION').upper() == 'VERSION':
+    os.environ['NCCL_DEBUG'] = 'WARN'
 
 WORKLOADS = {
     # name: (model, LR H, W, events per window, description)
@@ -357,7 +360,7 @@ def main():
     roofline = {'kernel': 'conv_slab2_tc (3x3 128->128 implicit GEMM, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
                 'traffic': NCU_CONV_TRAFFIC.get((model_kind, B, h, w)), 'traffic_unit': 'bytes per launch (ncu, profiles/r01_ncu_full_slab2_plain3x3.txt)',
-                'algorithmic_bytes': 2.0 * jobs * B * 128 * 2 * ((h + 2) * (w + 2) + 127) // 128 * 128,
+                'algorithmic_bytes': 2.0 * jobs * B * (((h + 2) * (w + 2) + 127) // 128 * 128) * 128 * 2,   # input read + output written
                 'us_per_launch': conv_ms * 1e3,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)'}
 
