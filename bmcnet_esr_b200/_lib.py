@@ -30,6 +30,8 @@ SIGNATURES = {
     'bmc_encode_workspace_bytes': (_sz, [_i64]),
     'bmc_encode_channels': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_channels_windows': (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _u, _vp]),
+    'bmc_encode_channels_windows_raw': (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i, _i, _i, _vp, _u, _vp]),
+    'bmc_format_events': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'bmc_encode_image': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_voxel': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_stack': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),

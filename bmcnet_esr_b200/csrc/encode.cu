@@ -426,6 +426,53 @@ __global__ void __launch_bounds__(256) channels_windows_kernel(
     for (int k = threadIdx.x; k < nb; k += blockDim.x) o[k] = s[k];
 }
 
+// Window pipeline of the dataloader on raw recordings (h5dataset.py:197-210 compute_k_indices, :407-414
+// get_events, base_dataset.py:24-31 event_formatting, h5dataset.py:518-526 create_cnt_encoding): window i is
+// events [stride*i, min(stride*i + window, n_events - 1)) of the int16 / float64 arrays as stored in the
+// HDF5 files (event_packagers.py:128-156), cast to float32 and counted like events_to_channels.  One CTA
+// per window; 12 B/event (2 + 2 + 8), no intermediate float arrays.
+__global__ void __launch_bounds__(256) channels_windows_raw_kernel(
+    const short* __restrict__ xs, const short* __restrict__ ys, const double* __restrict__ ps, long n_events,
+    long window, long stride, int H, int W, float* __restrict__ out, unsigned flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s = reinterpret_cast<float*>(smem_raw);
+    const int nb = 2 * H * W;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s[k] = 0.f;
+    __syncthreads();
+    const long b = stride * blockIdx.x;
+    long e = b + window;
+    if (e > n_events - 1) e = n_events - 1;
+    const bool quirks = !(flags & BMC_ENC_NO_QUIRKS);
+    for (long i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const float x = (float)xs[i], y = (float)ys[i], p = (float)ps[i];
+        Pix q = decode_xy(x, y, H, W, true);
+        const float w = p * p;
+        if (!q.oor) {
+            if (w != 0.f) atomicAdd(&s[(p < 0.f ? H * W : 0) + q.y * W + q.x], w);
+        } else if (quirks && p < 0.f) {
+            atomicAdd(&s[H * W + (H - 1) * W], w);
+        }
+    }
+    __syncthreads();
+    float* o = out + (long)blockIdx.x * nb;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) o[k] = s[k];
+}
+
+// BaseDataset.event_formatting (base_dataset.py:24-31): float32 casts and ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)
+// evaluated in float32 like the reference's tensor arithmetic -> out [4][n].
+__global__ void format_events_kernel(const short* __restrict__ xs, const short* __restrict__ ys,
+                                     const double* __restrict__ ts, const double* __restrict__ ps, long n,
+                                     float* __restrict__ out) {
+    const float t0 = (float)ts[0];
+    const float den = __fadd_rn(__fsub_rn((float)ts[n - 1], t0), 1e-6f);
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        out[i] = (float)xs[i];
+        out[n + i] = (float)ys[i];
+        out[2 * n + i] = __fdiv_rn(__fsub_rn((float)ts[i], t0), den);
+        out[3 * n + i] = (float)ps[i];
+    }
+}
+
 // ---------------------------------------------------------------- host-side launch logic
 struct Ws {
     int* cnt; float* ext; long* beg; long* end;
@@ -565,6 +612,37 @@ extern "C" BMC_EXPORT int bmc_encode_channels_windows(float* xs, float* ys, cons
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     channels_windows_kernel<<<n_windows, 256, smem, as_stream(stream)>>>(
         xs, ys, ps, reinterpret_cast<const long*>(offsets), H, W, out, flags);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+extern "C" BMC_EXPORT int bmc_encode_channels_windows_raw(const int16_t* xs, const int16_t* ys, const double* ps,
+                                                          int64_t n_events, int64_t window, int64_t stride, int n_windows,
+                                                          int H, int W, float* out, unsigned flags, void* stream) {
+    BMC_REQUIRE(n_windows >= 0 && H > 0 && W > 0 && out && xs && ys && ps, "encode_channels_windows_raw: bad args");
+    BMC_REQUIRE(window > 0 && stride > 0 && n_events >= 0, "encode_channels_windows_raw: window and stride must be positive");
+    BMC_REQUIRE(n_windows == 0 || stride * (int64_t)(n_windows - 1) <= n_events - 1,
+                "encode_channels_windows_raw: window %d starts past the recording (h5dataset.py:327-328)", n_windows - 1);
+    if (n_windows == 0) return BMC_OK;
+    const size_t smem = (size_t)2 * H * W * 4;
+    BMC_REQUIRE(smem <= (size_t)kSmemBudget, "encode_channels_windows_raw: a [2,%d,%d] window grid exceeds 227 KB of shared memory", H, W);
+    if (smem > 48 * 1024)
+        BMC_CUDA(cudaFuncSetAttribute(channels_windows_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    channels_windows_raw_kernel<<<n_windows, 256, smem, as_stream(stream)>>>(
+        reinterpret_cast<const short*>(xs), reinterpret_cast<const short*>(ys), ps, (long)n_events, (long)window, (long)stride,
+        H, W, out, flags);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+extern "C" BMC_EXPORT int bmc_format_events(const int16_t* xs, const int16_t* ys, const double* ts, const double* ps,
+                                            int64_t n, float* out, void* stream) {
+    BMC_REQUIRE(n >= 1 && xs && ys && ts && ps && out, "format_events: needs n >= 1 events (the reference indexes ts[0], ts[-1])");
+    long blocks = (n + 255) / 256;
+    const long cap = (long)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    format_events_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(reinterpret_cast<const short*>(xs),
+                                                                        reinterpret_cast<const short*>(ys), ts, ps, (long)n, out);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

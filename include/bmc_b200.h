@@ -76,6 +76,21 @@ int bmc_encode_channels_windows(float* xs, float* ys, const float* ps, const int
 /* events_to_image (encodings.py:241-269, with BMC_ENC_FLIP_Y) and events_to_image_torch
  * (encodings.py:16-72, without; BMC_ENC_BILINEAR selects the padded bilinear splat whose
  * output is float[H+1][W+1]).  Weighted fp32 scatter-add, out = device float[H][W]. */
+/* The dataloader's window pipeline on a raw recording, one launch: window i = events
+ * [stride*i, min(stride*i + window, n_events - 1)) (H5Dataset.compute_k_indices, h5dataset.py:197-210, with
+ * stride = window - sliding_window) of the arrays as stored on disk -- int16 xs, ys, float64 ps
+ * (event_packagers.py:128-156; get_events h5dataset.py:407-414) -- cast to float32
+ * (BaseDataset.event_formatting, base_dataset.py:24-31) and counted per polarity
+ * (create_cnt_encoding -> events_to_channels, h5dataset.py:518-526).  out: device float [n_windows][2][H][W]. */
+int bmc_encode_channels_windows_raw(const int16_t* xs, const int16_t* ys, const double* ps, int64_t n_events,
+                                    int64_t window, int64_t stride, int n_windows, int H, int W, float* out,
+                                    unsigned flags, void* stream);
+
+/* BaseDataset.event_formatting (base_dataset.py:24-31) on the device: out = float32 [4][n] =
+ * (xs, ys, (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6), ps), the division in float32 like the reference. */
+int bmc_format_events(const int16_t* xs, const int16_t* ys, const double* ts, const double* ps, int64_t n,
+                      float* out, void* stream);
+
 int bmc_encode_image(float* xs, float* ys, float* ps, int64_t n, int H, int W, float* out,
                      void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
 

@@ -172,9 +172,38 @@ def make_model_goldens():
                             n_unique_params=sum(p.numel() for p in m.parameters()))
 
 
+def synth_recording(n, h, w, seed, oor=0.0, t_base=1.6e9):
+    """Seeded raw recording as stored on disk: int16 xs / ys, float64 ts / ps (event_packagers.py:128-156)."""
+    g = np.random.default_rng(seed)
+    xs = g.integers(0, w, n).astype(np.int16)
+    ys = g.integers(0, h, n).astype(np.int16)
+    if oor > 0:
+        k = g.random(n) < oor
+        xs[k] = g.choice([-3, w, w + 5], int(k.sum())).astype(np.int16)
+        k = g.random(n) < oor
+        ys[k] = g.choice([-1, h, h + 2], int(k.sum())).astype(np.int16)
+    ts = np.sort(g.random(n) * 37.5 + t_base)         # float64 seconds; absolute epochs collapse in the float32 cast (base_dataset.py:28)
+    ps = g.choice([-1.0, 1.0], n)
+    return xs, ys, ts, ps
+
+
+def make_format_golden():
+    """BaseDataset.event_formatting of the reference on raw windows (base_dataset.py:24-31)."""
+    from dataloader.base_dataset import BaseDataset
+    out = {'torch_version': torch.__version__}
+    for name, n, seed, t_base in (('w2048', 2048, 31, 1.6e9), ('rel2048', 2048, 34, 0.25), ('w5', 5, 32, 3.0), ('w1', 1, 33, 0.0)):
+        xs, ys, ts, ps = synth_recording(n, 45, 80, seed, oor=0.05, t_base=t_base)
+        ev = np.concatenate((xs[np.newaxis], ys[np.newaxis], ts[np.newaxis], ps[np.newaxis]), axis=0)   # get_events, h5dataset.py:407-414
+        res = BaseDataset.event_formatting(ev)
+        out[name + '_xs'] = xs; out[name + '_ys'] = ys; out[name + '_ts'] = ts; out[name + '_ps'] = ps
+        out[name + '_out'] = res.numpy()
+    np.savez_compressed(os.path.join(GOLD, 'fmt_events.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     make_encoder_goldens()
     make_model_goldens()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print('golden bytes', total)
+    make_format_golden()

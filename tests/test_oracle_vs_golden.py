@@ -116,3 +116,27 @@ def test_state_dict_contract(golden_dir, plain):
     groups = [ptr.setdefault(sd[k].data_ptr(), len(ptr)) for k in keys]
     assert groups == [int(v) for v in g['alias_group']]
     assert sum(sd[r].numel() for r in {M._alias_root(k) for k in keys}) == int(g['n_unique_params'])
+
+
+# ---------------------------------------------------------------- dataloader window pipeline
+def test_event_formatting_oracle_bit_exact_vs_reference(golden_dir):
+    from oracle import h5windows_np as H
+    d = np.load(os.path.join(golden_dir, 'fmt_events.npz'))
+    for name in ('w2048', 'rel2048', 'w5', 'w1'):
+        got = H.event_formatting((d[name + '_xs'], d[name + '_ys'], d[name + '_ts'], d[name + '_ps']))
+        assert got.dtype == np.float32 and np.array_equal(got, d[name + '_out'], equal_nan=True), name
+
+
+@pytest.mark.parametrize('n,window,sliding', [(10000, 2048, 1024), (5000, 1024, 512), (2049, 2048, 1024), (100, 2048, 1024), (4096, 1024, 0)])
+def test_compute_k_indices_properties(n, window, sliding):
+    """h5dataset.py:169-175,197-210: int(n / stride) windows, starts stride apart, ends clipped to n - 1."""
+    from oracle import h5windows_np as H
+    from bmcnet_esr_b200.dataloader.h5windows import compute_k_indices
+    k = H.compute_k_indices(n, window, sliding)
+    assert k == compute_k_indices(n, window, sliding)
+    stride = window - sliding
+    assert len(k) == n // stride
+    for i, (a, b) in enumerate(k):
+        assert a == i * stride and b == min(a + window, n - 1) and b < n
+    assert H.compute_k_indices(n, window, sliding, dataset_length=1) == k[:1]
+    assert H.compute_k_indices(n, window, sliding, dataset_length=10 ** 9) == k
