@@ -61,12 +61,14 @@ __device__ __forceinline__ bool same_weights(const GemmJobDev& a, const GemmJobD
 struct Phase {
     int g, step, jn, r;             // r = g mod PH
     bool has_o, has_n, shared, t1, pm;
+    bool same_w;                    // both tiles in flight read the same static weights (changes with jn only)
     int job_o, job_n;
     long m_o, m_n;
     int groups, slots_per_group, n_act;
     int iw_slot, iw_par;            // weight ring position of the phase's first slot
 };
 
+template <int DBG>      // measurement builds (BMC_SLAB2_DBG): 1 = no operand movement (MMAs on stale shared memory), 2 = no epilogue stores
 __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -98,15 +100,20 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
     auto phase_first = [&](Phase& f) {
         f.g = 0; f.step = 0; f.jn = 0; f.r = 0; f.iw_slot = 0; f.iw_par = 0;
     };
+    // tiles / jobs change only when a tile starts (r == 0): the MMA threads run this between the last MMA of
+    // one phase and the first of the next, so per phase it is only a few bit tests
     auto phase_fill = [&](Phase& f) {
-        f.has_o = f.jn >= 1 && f.jn - 1 < n_mine;
-        f.has_n = f.jn < n_mine;
-        f.job_o = f.job_n = -1; f.m_o = f.m_n = 0;
-        if (f.has_o) tile_at(f.jn - 1, f.job_o, f.m_o);
-        if (f.has_n) tile_at(f.jn, f.job_n, f.m_n);
+        if (f.r == 0) {
+            f.has_o = f.jn >= 1 && f.jn - 1 < n_mine;
+            f.has_n = f.jn < n_mine;
+            f.job_o = f.job_n = -1; f.m_o = f.m_n = 0;
+            if (f.has_o) tile_at(f.jn - 1, f.job_o, f.m_o);
+            if (f.has_n) tile_at(f.jn, f.job_n, f.m_n);
+            f.n_act = (int)f.has_o + (int)f.has_n;
+            f.same_w = f.has_o && f.has_n && (f.job_o == f.job_n || same_weights(p.jobs[f.job_o], p.jobs[f.job_n], p.n_seg));
+        }
         f.t1 = (sp.t1 >> f.step) & 1u; f.pm = (sp.pm >> f.step) & 1u;
-        f.shared = f.has_o && f.has_n && !f.pm && (f.job_o == f.job_n || same_weights(p.jobs[f.job_o], p.jobs[f.job_n], p.n_seg));
-        f.n_act = (int)f.has_o + (int)f.has_n;
+        f.shared = f.same_w && !f.pm;
         f.groups = (f.t1 || n_taps == 1) ? 1 : 3;
         f.slots_per_group = f.shared ? 1 : f.n_act;
     };
@@ -134,7 +141,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
         // ------------------------------------------------------------ activation slabs: per phase the older tile's, then the newer's
         Phase f;
         phase_first(f);
-        for (; f.g < n_phases; phase_next(f)) {
+        for (; f.g < ((DBG & 1) ? 0 : n_phases); phase_next(f)) {
             phase_fill(f);
             const int sg = sp.seg[f.step];
             for (int e = 0; e < 2; ++e) {
@@ -160,7 +167,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
         Phase f;
         phase_first(f);
         int iw = 0;
-        for (; f.g < n_phases; phase_next(f)) {
+        for (; f.g < ((DBG & 1) ? 0 : n_phases); phase_next(f)) {
             phase_fill(f);
             const int sg = sp.seg[f.step];
             const int c0 = sp.col[f.step] & 63;               // column inside the 64-wide weight chunk
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
                 const int k = f.g - X * PH, st = 2 * X + (k & 1);              // my k-th slab
                 if (active) {
                     if (first && li >= 2) mbar_wait(&acc_empty[X], ((li >> 1) - 1) & 1);      // drained by the epilogue
-                    mbar_wait(&a_full[st], (k >> 1) & 1);
+                    if (!(DBG & 1)) mbar_wait(&a_full[st], (k >> 1) & 1);
                 }
                 const uint32_t slab_lo = slab_lo0 + st * slab_step;
                 int slot = f.iw_slot, wpar = f.iw_par;
@@ -231,7 +238,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
                     for (int ee = 0; ee < f.slots_per_group; ++ee) {
                         // a slot is read by both tiles (shared) or by the ee-th active tile in (older, newer) order
                         const bool mine = active && (f.shared || (f.has_o ? ee : 1) == e);
-                        mbar_wait(&w_full[slot], wpar);
+                        if (!(DBG & 1)) mbar_wait(&w_full[slot], wpar);
                         if (mine) {
                             tc_fence_after_sync();
                             const uint32_t w_lo = w_lo0 + slot * (kWSlot >> 4);
@@ -316,7 +323,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
                     // even lane: (mine.lo, theirs.lo)   odd lane: (theirs.hi, mine.hi)
                     const uint32_t o = (lane & 1) ? __byte_perm(theirs, mine, 0x7632) : __byte_perm(mine, theirs, 0x5410);
                     const long px = px_base + c * 32 + j + (lane & 1);
-                    if (px < rows_total) *reinterpret_cast<uint32_t*>(out + (long)(c * 32 + j) * kN) = o;
+                    if (px < rows_total && !(DBG & 2)) *reinterpret_cast<uint32_t*>(out + (long)(c * 32 + j) * kN) = o;
                 }
             }
         }
@@ -401,7 +408,10 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
     const int smem = slab2_smem(p.g, p.n_taps);
     static int configured = 0;
     if (configured < smem) {
-        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
     int grid = p.n_full < sm_count() ? p.n_full : sm_count();
@@ -410,7 +420,12 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
         if (cap < 0) { const char* e = getenv("BMC_SLABT_GRID"); cap = e ? atoi(e) : 0; }
         if (cap > 0 && grid > cap) grid = cap;
     }
-    conv_slab2_tc<<<grid, kThreads2, smem, st>>>(p);
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("BMC_SLAB2_DBG"); dbg = e ? atoi(e) : 0; }
+    if (dbg == 1) conv_slab2_tc<1><<<grid, kThreads2, smem, st>>>(p);
+    else if (dbg == 2) conv_slab2_tc<2><<<grid, kThreads2, smem, st>>>(p);
+    else if (dbg == 3) conv_slab2_tc<3><<<grid, kThreads2, smem, st>>>(p);
+    else conv_slab2_tc<0><<<grid, kThreads2, smem, st>>>(p);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
