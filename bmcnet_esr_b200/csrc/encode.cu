@@ -619,7 +619,9 @@ extern "C" BMC_EXPORT int bmc_encode_channels_windows(float* xs, float* ys, cons
 extern "C" BMC_EXPORT int bmc_encode_channels_windows_raw(const int16_t* xs, const int16_t* ys, const double* ps,
                                                           int64_t n_events, int64_t window, int64_t stride, int n_windows,
                                                           int H, int W, float* out, unsigned flags, void* stream) {
-    BMC_REQUIRE(n_windows >= 0 && H > 0 && W > 0 && out && xs && ys && ps, "encode_channels_windows_raw: bad args");
+    BMC_REQUIRE(n_windows >= 0 && H > 0 && W > 0, "encode_channels_windows_raw: bad sizes");
+    if (n_windows == 0) return BMC_OK;
+    BMC_REQUIRE(out && xs && ys && ps, "encode_channels_windows_raw: NULL argument");
     BMC_REQUIRE(window > 0 && stride > 0 && n_events >= 0, "encode_channels_windows_raw: window and stride must be positive");
     BMC_REQUIRE(n_windows == 0 || stride * (int64_t)(n_windows - 1) <= n_events - 1,
                 "encode_channels_windows_raw: window %d starts past the recording (h5dataset.py:327-328)", n_windows - 1);

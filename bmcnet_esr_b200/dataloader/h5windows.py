@@ -62,6 +62,8 @@ def windows_to_counts(xs, ys, ps, window, sliding_window, sensor_size, dataset_l
     n_win = len(compute_k_indices(n, window, sliding_window, dataset_length))
     h, w = sensor_size
     out = torch.empty(n_win, 2, h, w, dtype=torch.float32, device=xs.device)
+    if n_win == 0:                       # recording shorter than one stride (the reference raises on length 0, h5dataset.py:194-195)
+        return out
     with torch.cuda.device(xs.device):
         _lib.check(_lib.lib().bmc_encode_channels_windows_raw(C.c_void_p(xs.data_ptr()), C.c_void_p(ys.data_ptr()),
                                                               C.c_void_p(ps.data_ptr()), n, window, stride, n_win, h, w,

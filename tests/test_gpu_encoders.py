@@ -173,3 +173,47 @@ def test_fp32_saturation_matches_reference_semantics(G):
     ps = torch.ones(n, device='cuda')
     out = G.events_to_channels(xs, ys, ps, sensor_size=(4, 4))
     assert float(out[0, 4 - 1 - 1, 2]) == float(1 << 24)
+
+
+def test_full_size_voxel_and_stack_properties(G):
+    """BASELINE-size streams (1e8 events) through the float and the binned encoders: properties that need no
+    CPU oracle -- mass conservation, additivity over a split of the stream, the y-flip identity between the two
+    voxel entry points, and the bin structure of the stack encoders."""
+    n, h, w, B = 100_000_000, 45, 80, 5
+    g = torch.Generator(device='cuda').manual_seed(2)
+    xs = torch.floor(torch.rand(n, device='cuda', generator=g) * w)
+    ys = torch.floor(torch.rand(n, device='cuda', generator=g) * h)
+    ps = (torch.rand(n, device='cuda', generator=g) < 0.5).float() * 2 - 1
+    ts = torch.sort(torch.rand(n, device='cuda', generator=g))[0]
+    ts = (ts - ts[0]) / (ts[-1] - ts[0] + 1e-6)
+    vox = G.events_to_voxel(xs, ys, ts, ps, B, sensor_size=(h, w))
+    # the two temporal weights of an event sum to 1: total mass = sum(p) (fp32 bins, fp64 reduction)
+    assert abs(float(vox.sum(dtype=torch.float64)) - float(ps.sum(dtype=torch.float64))) <= 1e-6 * n
+    k = 41_234_567
+    parts = G.events_to_voxel(xs[:k].contiguous(), ys[:k].contiguous(), ts[:k].contiguous(), ps[:k].contiguous(), B, sensor_size=(h, w)) + \
+        G.events_to_voxel(xs[k:].contiguous(), ys[k:].contiguous(), ts[k:].contiguous(), ps[k:].contiguous(), B, sensor_size=(h, w))
+    scale = float(vox.abs().max())
+    assert float((vox - parts).abs().max()) <= 2e-5 * scale           # ~5500 fp32 additions per bin in another order
+    # events_to_voxel_torch == flip(events_to_voxel) on pre-normalised ts (SURVEY 8a E8)
+    vt = G.events_to_voxel_torch(xs, ys, ts, ps, B, sensor_size=(h, w))
+    assert float((vt - torch.flip(vox, dims=[1])).abs().max()) <= 2e-5 * scale
+    # large grid: the pair-reduction path agrees with the shared-memory path on the same events (coordinates x1)
+    big = G.events_to_voxel(xs[:20_000_000].contiguous(), ys[:20_000_000].contiguous(), ts[:20_000_000].contiguous(),
+                            ps[:20_000_000].contiguous(), B, sensor_size=(180, 320))
+    small = G.events_to_voxel(xs[:20_000_000].contiguous(), ys[:20_000_000].contiguous(), ts[:20_000_000].contiguous(),
+                              ps[:20_000_000].contiguous(), B, sensor_size=(h, w))
+    # y-flip: row H-1-y of the small grid is row 179-y of the large one; columns coincide
+    assert float((big[:, 180 - h:, :w] - small).abs().max()) <= 2e-5 * float(small.abs().max())
+    assert float(big[:, :180 - h].abs().max()) == 0.0 and float(big[:, :, w:].abs().max()) == 0.0
+    # stack encoders: every event lands in >= 1 bin, boundary events in two (SURVEY F10); polarity planes are counts
+    st = G.events_to_stack_polarity(xs, ys, ts, ps, B, sensor_size=(h, w))
+    total = float(st.sum(dtype=torch.float64))
+    assert n <= total <= n + 2 * B
+    assert float(st.min()) >= 0.0
+    sn = G.events_to_stack_no_polarity(xs, ys, ts, ps, B, sensor_size=(h, w))
+    assert torch.equal(sn, st[0] - st[1])
+    # bins partition time: bin b of the stack equals the count image of the events in its time slice
+    edges = torch.searchsorted(ts, torch.linspace(0, 1, B + 1, device='cuda')[1:-1].contiguous())
+    lo, hi = int(edges[1]) + 8, int(edges[2]) - 8                     # strictly inside bin 2
+    mid = G.events_to_image_torch(xs[lo:hi].contiguous(), ys[lo:hi].contiguous(), ps[lo:hi].contiguous(), sensor_size=(h, w))
+    assert float((sn[2] - mid).abs().max()) <= 16.0                   # up to 8 events on either side of the slice

@@ -205,3 +205,29 @@ def test_resident_state_fast_path_equals_repacking(plain_ckpt):
         a = m(xs[1], *st, False)
         bb = m(xs[1], *[t.clone() for t in st], False)
         assert torch.equal(a[-1], bb[-1]) and not torch.equal(a[-1], fast[1][-1])
+
+
+def test_sequences_of_a_batch_are_independent_at_bench_size(plain_ckpt):
+    """Inference shards by independent sequences: at the bench batch (57 sequences, tiles
+    straddling images, per-image attention partials spread over CTAs) every sequence must get what it gets when
+    stepped alone -- up to the summation order of the attention partials."""
+    _, BMCNet_plain = _models()
+    m = BMCNet_plain(4, 128, 5)
+    m.load_state_dict(plain_ckpt, strict=True)
+    m = m.cuda().eval()
+    b, h, w = 57, 45, 80
+    xs = [synth_counts(b, h, w, 100 + s).cuda() for s in range(2)]
+    st = [torch.zeros(b, 128, h, w).cuda(), torch.zeros(b, 32, h, w).cuda()]
+    init = True
+    for x in xs:
+        st = list(m(x, *st, init))
+        init = False
+    for pick in (0, 31, 56):
+        s1 = [torch.zeros(1, 128, h, w).cuda(), torch.zeros(1, 32, h, w).cuda()]
+        init = True
+        for x in xs:
+            s1 = list(m(x[pick:pick + 1], *s1, init))
+            init = False
+        for full, one in zip(st, s1):
+            err = (full[pick:pick + 1] - one).abs().max().item()
+            assert err <= 2e-3 * max(1.0, one.abs().max().item()), (pick, err)
