@@ -11,8 +11,9 @@
 //
 // Accumulator: TMEM lane = output channel, column = pixel of the tile (2 x 256 columns, double
 // buffered).  The epilogue therefore owns a CHANNEL per thread and 32 consecutive pixels per
-// tcgen05.ld; bias is a per-thread scalar, the halo mask a per-column bit, and the [32 px x 32 ch]
-// fp16 block is transposed through a 2 KB shared-memory tile so global stores stay row-contiguous.
+// tcgen05.ld; bias is a per-thread scalar, the halo mask a per-column bit; lane pairs swap halves so that
+// every lane stores two adjacent channels of one pixel (a warp store covers two 64-byte runs) -- the
+// shared-memory transposition this replaced cost 128 KB of staging traffic per tile (mix launch 141 -> 135 us).
 // Supported: N = 128 outputs, 16-bit output only, no epilogue residual / LayerNorm / fp32 side output
 // (the fused plan needs none of them: residuals are identity K segments); everything else falls back
 // to conv_slab_tc.  K steps, slab views, weight stages and the tile schedule are those of gemm_slab.cu.
@@ -266,26 +267,22 @@ __global__ void __launch_bounds__(kThreadsT, 1) conv_slabt_tc(const __grid_const
                     int y, x;
                     valid_mask = __ballot_sync(0xffffffffu, m < rows_total && p.g.interior(r_img, y, x));
                 }
-                // transpose [channel = lane][pixel j] -> stage[pixel j][channel lane]
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float f = __uint_as_float(v[j]) + bias_c;
-                    if (relu) f = fmaxf(f, 0.f);
-                    if (!((valid_mask >> j) & 1u)) f = 0.f;
-                    *reinterpret_cast<act_t*>(stage + j * 64 + lane * 2) = to_act(f);
-                }
-                __syncwarp();
+                // lane pairs swap halves: even lanes end up with channels (ch, ch+1) of pixel j, odd lanes with
+                // (ch-1, ch) of pixel j+1; a warp store covers two 64-byte runs (no shared-memory staging)
                 {
-                    const int crow = lane >> 2, cpiece = lane & 3;     // pixel crow + 8 i, 16-byte piece of its 64-byte channel run
-                    act_t* out = job.out + (job.out_row_base + px0) * kN + q * 32 + cpiece * 8;
+                    act_t* out = job.out + (job.out_row_base + px0 + (lane & 1)) * kN + (ch & ~1);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = crow + 8 * i;
-                        const uint4 ov = *reinterpret_cast<const uint4*>(stage + row * 64 + cpiece * 16);
-                        if (px0 + row < rows_total) *reinterpret_cast<uint4*>(out + (long)row * kN) = ov;
+                    for (int j = 0; j < 32; j += 2) {
+                        float f0 = __uint_as_float(v[j]) + bias_c, f1 = __uint_as_float(v[j + 1]) + bias_c;
+                        if (relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+                        if (!((valid_mask >> j) & 1u)) f0 = 0.f;
+                        if (!((valid_mask >> (j + 1)) & 1u)) f1 = 0.f;
+                        const uint32_t mine = pack_act2(f0, f1);
+                        const uint32_t theirs = __shfl_xor_sync(0xffffffffu, mine, 1);
+                        const uint32_t o = (lane & 1) ? __byte_perm(theirs, mine, 0x7632) : __byte_perm(mine, theirs, 0x5410);
+                        if (px0 + j + (lane & 1) < rows_total) *reinterpret_cast<uint32_t*>(out + (long)j * kN) = o;
                     }
                 }
-                __syncwarp();
             }
         }
     }
