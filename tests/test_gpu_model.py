@@ -231,3 +231,38 @@ def test_sequences_of_a_batch_are_independent_at_bench_size(plain_ckpt):
         for full, one in zip(st, s1):
             err = (full[pick:pick + 1] - one).abs().max().item()
             assert err <= 2e-3 * max(1.0, one.abs().max().item()), (pick, err)
+
+
+def test_bmcnet_sequences_independent_many_tiles(plain_ckpt):
+    """Full BMCNet at a batch with many tiles per CTA: launches of 4 jobs with two weight sets, so the two tiles a
+    CTA of conv_slab2_tc has in flight read different weights at job boundaries (non-shared weight slots)."""
+    BMCNet, _ = _models()
+    sd = O.surrogate_state_dict(plain=False, transplant=plain_ckpt)
+    m = BMCNet(4, 128, 5)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    b, h, w = 38, 45, 80
+    xs = [synth_counts(b, h, w, 200 + s).cuda() for s in range(2)]
+
+    def run(sel):
+        n = len(sel)
+        st = [torch.zeros(n, 128, h, w).cuda() for _ in range(3)] + [torch.zeros(n, 32, h, w).cuda()]
+        init = True
+        for x in xs:
+            st = list(m(x[sel], *st, init))
+            init = False
+        return st
+
+    full = run(list(range(b)))
+    for pick in (0, 20, 37):
+        one = run([pick])
+        for f, o in zip(full, one):
+            err = (f[pick:pick + 1] - o).abs().max().item()
+            assert err <= 2e-3 * max(1.0, o.abs().max().item()), (pick, err)
+    # and against the fp32 oracle for one of the sequences (2 steps)
+    ref = [torch.zeros(1, 128, h, w) for _ in range(3)] + [torch.zeros(1, 32, h, w)]
+    init = True
+    for x in xs:
+        ref = list(O.bmcnet_forward(sd, x[20:21].cpu(), *ref, init))
+        init = False
+    _check_step([t[20:21] for t in full], ref, xs[-1][20:21].cpu(), 'bmcnet B=38 seq 20')
