@@ -47,9 +47,10 @@ WORKLOADS = {
 }
 CONV_MAC_PER_PX = 147456          # 3x3 128->128
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_ncu_full_*.txt):
-# conv_slab2_tc, 2 jobs, B=57, 45x80: 116.2 + 69.3 MB (algorithmic 115.8 read + 115.8 written; part of the output is
-# still dirty in L2 when the kernel ends); encoders: bytes per event at 1e8 events (12.04 / 16.04 for 12 / 16 algorithmic)
-NCU_CONV_TRAFFIC = {('plain', 57, 45, 80): 185.5e6}
+# conv_slab2_tc, 2 jobs, 45x80: B=95: 193.5 + 146.4 MB (algorithmic 193.0 read + 193.0 written; part of the output is
+# still dirty in L2 when the kernel ends), B=57: 116.2 + 70.5 MB; encoders: bytes per event at 1e8 events
+# (12.04 / 16.04 for 12 / 16 algorithmic)
+NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): 339.9e6, ('plain', 57, 45, 80): 186.7e6}
 NCU_ENC_BYTES_PER_EVENT, NCU_VOX_BYTES_PER_EVENT = 12.045, 16.035
 FLOP_PER_PX = {'plain': 9721856, 'full': 41574912}      # SURVEY 8d / BASELINE.md section 3
 
@@ -169,8 +170,9 @@ def main():
     if args.batch <= 0:
         # tiles per conv job = ceil(B * R / 256), R = roundup((H+2)(W+2), 128): multiples of 19 images give
         # 19 x 3968 / 256 = 294.5 ~ 2 x 148 tiles per job (whole waves of the 148 SMs); larger batches amortise
-        # the per-launch prologue (measured: plain 20.0k / 22.3k / 23.3k frames/s at B = 19 / 38 / 57)
-        args.batch = {'plain_nfs': 57, 'bmcnet_nfs': 38, 'bmcnet_eventzoom': 78}[args.workload]
+        # the per-launch prologue (measured: plain 20.0k / 22.3k / 23.5k / 24.6k / 24.7k frames/s at B = 19 / 38 / 57 / 76 / 95,
+        # BMCNet 5.86k / 6.11k / 6.21k at B = 38 / 57 / 76)
+        args.batch = {'plain_nfs': 95, 'bmcnet_nfs': 76, 'bmcnet_eventzoom': 156}[args.workload]
     config = {'workload': desc, 'batch_per_gpu': args.batch, 'lr_hw': [h, w], 'events_per_window': n_win,
               'windows_per_step_per_sequence': 2, 'sharding': 'independent sequences per GPU, no collective'}
 
