@@ -204,6 +204,23 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
         : "r"(taddr)
         : "memory");
 }
+// 16 lanes x (8 columns x 4 repetitions): the mma-accumulator fragment layout -- per repetition k thread t holds
+// (lane t/4, columns 8k + 2(t%4), +1) in v[4k], v[4k+1] and (lane t/4 + 8, same columns) in v[4k+2], v[4k+3].
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+// Four 8x8 b16 matrices, transposed on the way: lane l supplies the shared-memory address of row (l % 8) of matrix
+// (l / 8); the thread's fragment of matrix m is register m (row t/4, columns 2(t%4), +1 of the UNtransposed matrix).
+__device__ __forceinline__ void stmatrix_x4_trans(void* smem_row, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+                 ::"r"(smem_u32(smem_row)), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }

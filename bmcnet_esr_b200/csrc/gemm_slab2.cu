@@ -76,6 +76,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
     const int n_boxes = p.slab_boxes;
     const int slab_bytes = n_boxes * p.abox32_rows * kRowBytes;
     uint8_t* smem_w = smem + S * slab_bytes;
+    uint8_t* smem_stage = smem_w + kWSlots * kWSlot;               // 8 epilogue warps x 2 KB (stmatrix epilogue)
 
     __shared__ uint64_t a_full[S], a_empty[S], w_full[kWSlots], w_empty[kWSlots];
     __shared__ uint64_t acc_full[2], acc_empty[2];
@@ -300,6 +301,61 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
             mbar_wait(&acc_full[buf], (li >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t trow = tmem_base + buf * 256 + ph * 128 + ((uint32_t)(q * 32) << 16);
+            if (DBG & 8) {
+                // stmatrix epilogue: the accumulator is read in the mma-fragment layout (16 lanes x 8 columns per
+                // repetition), packed to 16 bits and written TRANSPOSED into a [32 px][32 ch] staging tile with four
+                // stmatrix per 32-pixel chunk, then leaves as 16-byte stores (64 contiguous bytes per pixel): 14
+                // memory-queue instructions per thread and chunk instead of 16 shuffles + 16 4-byte stores.
+                uint32_t f[4][2][16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(trow + c * 32 + ((uint32_t)(hf * 16) << 16), f[c][hf]);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                uint8_t* stage = smem_stage + warp * 2048;
+                const int tr = lane >> 2, tc2 = (lane & 3) * 2;            // fragment row (channel) and first column (pixel)
+                float bia[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chn = q * 32 + g * 8 + tr;
+                    bia[g] = (job.bias ? job.bias[chn] : 0.f) + (job.bias_img ? job.bias_img[img_h * kN + chn] : 0.f);
+                }
+                const int crow = lane >> 2, cchunk = lane & 3;              // store mapping: pixel crow + 8 i, 16-byte piece cchunk
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t plo[4], phi[4];                             // channel groups g = 2 hf (lanes 0-7 of the half) and 2 hf + 1
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int col = 8 * k + tc2;
+                            const bool v0 = (valid[c] >> col) & 1u, v1 = (valid[c] >> (col + 1)) & 1u;
+                            float a0 = __uint_as_float(f[c][hf][4 * k]) + bia[2 * hf], a1 = __uint_as_float(f[c][hf][4 * k + 1]) + bia[2 * hf];
+                            float b0 = __uint_as_float(f[c][hf][4 * k + 2]) + bia[2 * hf + 1], b1 = __uint_as_float(f[c][hf][4 * k + 3]) + bia[2 * hf + 1];
+                            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
+                            plo[k] = pack_act2(v0 ? a0 : 0.f, v1 ? a1 : 0.f);
+                            phi[k] = pack_act2(v0 ? b0 : 0.f, v1 ? b1 : 0.f);
+                        }
+                        // lane l addresses pixel l of the chunk (matrix l/8 = pixel group, row l%8); chunk index swizzled
+                        // with the pixel so that the 8 rows of a matrix and the 16-byte reads below are conflict-free
+                        const int sw = (lane >> 1) & 3;
+                        stmatrix_x4_trans(stage + lane * 64 + (((2 * hf) ^ sw) << 4), plo[0], plo[1], plo[2], plo[3]);
+                        stmatrix_x4_trans(stage + lane * 64 + (((2 * hf + 1) ^ sw) << 4), phi[0], phi[1], phi[2], phi[3]);
+                    }
+                    __syncwarp();
+                    act_t* o16 = job.out + (job.out_row_base + px_base + c * 32) * kN + q * 32 + cchunk * 8;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int row = crow + 8 * i;
+                        const uint4 ov = *reinterpret_cast<const uint4*>(stage + row * 64 + ((cchunk ^ ((row >> 1) & 3)) << 4));
+                        if (px_base + c * 32 + row < rows_total) *reinterpret_cast<uint4*>(o16 + (long)row * kN) = ov;
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
             uint32_t v[4][32];
 #pragma unroll
             for (int c = 0; c < 4; ++c) tmem_ld_32x32(trow + c * 32, v[c]);
@@ -323,6 +379,12 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
                     // even lane: (mine.lo, theirs.lo)   odd lane: (theirs.hi, mine.hi)
                     const uint32_t o = (lane & 1) ? __byte_perm(theirs, mine, 0x7632) : __byte_perm(mine, theirs, 0x5410);
                     const long px = px_base + c * 32 + j + (lane & 1);
+                    if (DBG & 4) {          // measurement: same bytes in a quarter of the store instructions (16-byte stores of garbage)
+                        if ((j & 6) == 0 && px + 6 < rows_total) {
+                            uint4* a16 = reinterpret_cast<uint4*>(reinterpret_cast<uintptr_t>(out + (long)(c * 32 + j) * kN) & ~(uintptr_t)15);
+                            *a16 = make_uint4(o, o, o, o);
+                        }
+                    } else
                     if (px < rows_total && !(DBG & 2)) *reinterpret_cast<uint32_t*>(out + (long)(c * 32 + j) * kN) = o;
                 }
             }
@@ -357,7 +419,7 @@ static int slab2_boxes(const Geom& g, int n_taps) {
 }
 
 static int slab2_smem(const Geom& g, int n_taps) {
-    return kSlabStages * slab2_boxes(g, n_taps) * slab2_box_rows(g, n_taps) * kRowBytes + kWSlots * kWSlot + 1024;
+    return kSlabStages * slab2_boxes(g, n_taps) * slab2_box_rows(g, n_taps) * kRowBytes + kWSlots * kWSlot + 8 * 2048 + 1024;
 }
 
 bool slab2_supported(const GemmParams& p) {
@@ -412,6 +474,8 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
     int grid = p.n_full < sm_count() ? p.n_full : sm_count();
@@ -425,6 +489,8 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
     if (dbg == 1) conv_slab2_tc<1><<<grid, kThreads2, smem, st>>>(p);
     else if (dbg == 2) conv_slab2_tc<2><<<grid, kThreads2, smem, st>>>(p);
     else if (dbg == 3) conv_slab2_tc<3><<<grid, kThreads2, smem, st>>>(p);
+    else if (dbg == 4) conv_slab2_tc<4><<<grid, kThreads2, smem, st>>>(p);
+    else if (dbg == 8) conv_slab2_tc<8><<<grid, kThreads2, smem, st>>>(p);
     else conv_slab2_tc<0><<<grid, kThreads2, smem, st>>>(p);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
