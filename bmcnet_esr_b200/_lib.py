@@ -52,6 +52,10 @@ SIGNATURES = {
     'bmc_layernorm_rows': (_i, [_vp, _vp, _vp, _f, _i64, _vp, _vp]),
     'bmc_pack_nchw': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp]),
     'bmc_unpack_nchw': (_i, [_vp, _i, _i, _i, _i, _i, _i, _vp, _vp]),
+    'bmc_stack_to_events_workspace_bytes': (_sz, [_i, _i64, _i64]),
+    'bmc_stack_event_counts': (_i, [_vp, _i, _i64, _vp, _sz, _vp, _vp, _vp]),
+    'bmc_stack_to_events': (_i, [_vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    'bmc_stack2cnt': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'bmc_sr_metrics': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
 }
 

@@ -23,7 +23,9 @@ from .._lib import check, lib, stream_ptr
 
 __all__ = ['interpolate_to_image', 'events_to_image_torch', 'binary_search_torch_tensor',
            'events_to_voxel_torch', 'events_to_stack_polarity', 'events_to_stack_no_polarity',
-           'events_to_image', 'events_to_voxel', 'events_to_channels', 'events_to_channels_windows']
+           'events_to_image', 'events_to_voxel', 'events_to_channels', 'events_to_channels_windows',
+           'python_event_redistribute_PolarityStack', 'python_event_redistribute_NoPolarityStack', 'stack2cnt',
+           'event_restore']
 
 _MUT = _lib.ENC_MUTATE
 
@@ -204,3 +206,73 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
     out = _run(lambda *a: lib().bmc_encode_voxel(_p(xs), _p(ys), _p(ts), _p(ps), n, B, h, w, *a, flags,
                                                  stream_ptr()), out)
     return out.to(device)
+
+
+# ---------------------------------------------------------------------------------------------- inverse encoders
+def _redistribute(event_stack, mode, polarity):
+    if not isinstance(event_stack, torch.Tensor) or not event_stack.is_cuda or event_stack.dtype != torch.float32:
+        raise _lib.BmcError('event stacks must be CUDA float32 tensors (no CPU fallback)')
+    want = 5 if polarity else 4
+    if event_stack.dim() != want:
+        raise _lib.BmcError('expected a %d-D stack, got %s' % (want, tuple(event_stack.shape)))
+    if mode not in ('linear', 'random'):
+        raise ValueError(mode)
+    st = event_stack.contiguous()
+    b = st.shape[0]
+    p = 2 if polarity else 1
+    c, y, x = st.shape[-3:]
+    if polarity and st.shape[1] != 2:
+        raise _lib.BmcError('polarity stacks are [B, 2, C, Y, X]')
+    per_entry = p * c * y * x
+    dev = st.device
+    with torch.cuda.device(dev):
+        nb0 = lib().bmc_stack_to_events_workspace_bytes(b, per_entry, 0)
+        ws0 = torch.empty(nb0, dtype=torch.uint8, device=dev)
+        counts = torch.empty(2, b, dtype=torch.int64, device=dev)
+        check(lib().bmc_stack_event_counts(_p(st), b, per_entry, _p(ws0), nb0, _p(counts[0]), _p(counts[1]), stream_ptr()))
+        totals, sums = counts.tolist()                      # the output SHAPE depends on them (reference: maxlen, :405-408)
+        if sum(sums) == 0:                                  # `if event_stack.sum() != 0` (:380,429)
+            return torch.zeros(b, 1, 4, device=dev)
+        maxlen = max(t if s != 0 else 1 for t, s in zip(totals, sums))
+        nb = lib().bmc_stack_to_events_workspace_bytes(b, per_entry, maxlen)
+        ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+        out = torch.empty(b, maxlen, 4, dtype=torch.float32, device=dev)
+        rnd = torch.rand(b, maxlen, device=dev) if mode == 'random' else None
+        check(lib().bmc_stack_to_events(_p(st), b, p, c, y, x, maxlen, _p(rnd) if rnd is not None else None, _p(out),
+                                        _p(ws), nb, stream_ptr()))
+    return out
+
+
+def python_event_redistribute_PolarityStack(event_stack, mode='linear'):
+    """[B, 2, C, Y, X] count stack -> batched event cloud [B, max_num_event, 4] = (x, y, t, p), each entry stably
+    sorted by t and zero-padded (reference encodings.py:367-414).  mode='random' draws its own uniform numbers
+    (torch.rand on the device), so only its distribution matches the reference."""
+    return _redistribute(event_stack, mode, True)
+
+
+def python_event_redistribute_NoPolarityStack(event_stack, mode='linear'):
+    """[B, C, Y, X] signed count stack -> batched event cloud [B, max_num_event, 4] (reference encodings.py:417-464)."""
+    return _redistribute(event_stack, mode, False)
+
+
+def stack2cnt(stack):
+    """[B, TB, H, W] signed stack -> [B, 2, H, W] positive / negative counts (reference encodings.py:653-671)."""
+    if not isinstance(stack, torch.Tensor) or not stack.is_cuda or stack.dtype != torch.float32 or stack.dim() != 4:
+        raise _lib.BmcError('stack2cnt needs a 4-D CUDA float32 tensor (no CPU fallback)')
+    st = stack.contiguous()
+    b, tb, h, w = st.shape
+    out = torch.empty(b, 2, h, w, dtype=torch.float32, device=st.device)
+    with torch.cuda.device(st.device):
+        check(lib().bmc_stack2cnt(_p(st), b, tb, h, w, _p(out), stream_ptr()))
+    return out
+
+
+def event_restore(events, resolution):
+    """[B, N, 4] normalised (x, y, t, p) -> pixel coordinates and +-1 polarities (reference encodings.py:581-602);
+    elementwise tensor glue, stays on the caller's device."""
+    events = events.detach().clone()
+    x = events[:, :, 0] * resolution[1]
+    y = events[:, :, 1] * resolution[0]
+    t = events[:, :, 2]
+    p = torch.sign(events[:, :, 3])
+    return torch.stack([x, y, t, p], dim=2)

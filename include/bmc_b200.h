@@ -233,6 +233,25 @@ int bmc_unpack_nchw(const void* src_act16, int B, int C, int H, int W, int c_pad
                     float* dst, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Inverse encoders (reference dataloader/encodings.py:367-464, 653-671): count stacks back to event clouds.
+ *   bmc_stack_event_counts  per-entry totals sum(|round(v)|) and sum(round(v)) -- what the reference derives its
+ *                           maxlen and its `entry.sum() != 0` tests from (:383,386,432,435); device int64[B] each.
+ *   bmc_stack_to_events     python_event_redistribute_PolarityStack (P = 2, stack [B,2,C,Y,X]) /
+ *                           _NoPolarityStack (P = 1, stack [B,C,Y,X]): out = device float [B][maxlen][4] =
+ *                           (x, y, t, p) per entry, stably sorted by t, zero-padded; timestamps
+ *                           torch.linspace(c/C + 1/(100 C), (c+1)/C, |v|) (rnd == NULL, mode='linear') or
+ *                           rnd * (t1 - t0) + t0 with rnd = device float [B][maxlen] uniform numbers (mode='random').
+ *   bmc_stack2cnt           stack2cnt (:653-671): [B,TB,H,W] -> [B,2,H,W].
+ * The workspace (256-byte aligned, bmc_stack_to_events_workspace_bytes) is caller-owned scratch.
+ * ---------------------------------------------------------------------------------------- */
+size_t bmc_stack_to_events_workspace_bytes(int B, int64_t per_entry, int64_t maxlen);
+int bmc_stack_event_counts(const float* stack, int B, int64_t per_entry, void* workspace, size_t workspace_bytes,
+                           int64_t* totals_out, int64_t* sums_out, void* stream);
+int bmc_stack_to_events(const float* stack, int B, int P, int C, int Y, int X, int64_t maxlen, const float* rnd,
+                        float* out, void* workspace, size_t workspace_bytes, void* stream);
+int bmc_stack2cnt(const float* stack, int B, int TB, int H, int W, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Evaluation tail of the inference loop (reference infer_BMCNet.py:77-87), on the device:
  *   sums[0] = sum((resize(pred) - gt)^2)   resize = bicubic to the gt size when the sizes differ (:78-79)
  *   sums[1] = sum((bicubic(inp) - gt)^2)   the bicubic baseline of the LR count frame (:80)

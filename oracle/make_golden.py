@@ -200,6 +200,31 @@ def make_format_golden():
     np.savez_compressed(os.path.join(GOLD, 'fmt_events.npz'), **out)
 
 
+def synth_stack(b, shape, seed, rate=0.15, vmax=4):
+    """Seeded count stack with sparse small integers plus fractional noise (the functions round first)."""
+    g = torch.Generator().manual_seed(seed)
+    v = torch.randint(-vmax, vmax + 1, (b,) + shape, generator=g).float()
+    keep = torch.rand((b,) + shape, generator=g) < rate
+    return v * keep + (torch.rand((b,) + shape, generator=g) - 0.5) * 0.6
+
+
+def make_redistribute_golden():
+    """The reference's inverse encoders on small stacks (encodings.py:367-464, 653-671)."""
+    from dataloader import encodings as R
+    out = {'torch_version': torch.__version__}
+    pol = synth_stack(3, (2, 4, 6, 7), 41).abs()                       # per-polarity counts are non-negative
+    pol[2] = 0                                                         # an empty entry
+    nop = synth_stack(3, (5, 6, 7), 42)
+    nop[1] = 0
+    nop[1, 0, 0, 0], nop[1, 1, 2, 3] = 2.0, -2.0                       # sums to zero: the reference treats it as empty
+    out['pol_in'] = pol.numpy(); out['pol_out'] = R.python_event_redistribute_PolarityStack(pol.clone()).numpy()
+    out['nop_in'] = nop.numpy(); out['nop_out'] = R.python_event_redistribute_NoPolarityStack(nop.clone()).numpy()
+    zero = torch.zeros(2, 3, 4, 5)
+    out['zero_out'] = R.python_event_redistribute_NoPolarityStack(zero).numpy()
+    out['s2c_in'] = nop.numpy(); out['s2c_out'] = R.stack2cnt(nop.clone()).numpy()
+    np.savez_compressed(os.path.join(GOLD, 'redistribute.npz'), **out)
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     make_encoder_goldens()
@@ -207,3 +232,4 @@ if __name__ == '__main__':
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print('golden bytes', total)
     make_format_golden()
+    make_redistribute_golden()

@@ -140,3 +140,13 @@ def test_compute_k_indices_properties(n, window, sliding):
         assert a == i * stride and b == min(a + window, n - 1) and b < n
     assert H.compute_k_indices(n, window, sliding, dataset_length=1) == k[:1]
     assert H.compute_k_indices(n, window, sliding, dataset_length=10 ** 9) == k
+
+
+# ---------------------------------------------------------------- inverse encoders
+def test_redistribute_oracle_exact_vs_reference(golden_dir):
+    from oracle import redistribute_ref as R
+    d = np.load(os.path.join(golden_dir, 'redistribute.npz'))
+    assert np.array_equal(R.event_redistribute(torch.from_numpy(d['pol_in']), True).numpy(), d['pol_out'])
+    assert np.array_equal(R.event_redistribute(torch.from_numpy(d['nop_in']), False).numpy(), d['nop_out'])
+    assert np.array_equal(R.event_redistribute(torch.zeros(2, 3, 4, 5), False).numpy(), d['zero_out'])
+    assert np.array_equal(R.stack2cnt(torch.from_numpy(d['s2c_in'])).numpy(), d['s2c_out'])
