@@ -11,7 +11,7 @@ import torch
 
 from .. import _lib
 
-__all__ = ['compute_k_indices', 'event_formatting', 'windows_to_counts']
+__all__ = ['compute_k_indices', 'event_formatting', 'windows_to_counts', 'sequence_tuples', 'sequence_item']
 
 
 def compute_k_indices(num_events, window, sliding_window, dataset_length=None):
@@ -69,3 +69,25 @@ def windows_to_counts(xs, ys, ps, window, sliding_window, sensor_size, dataset_l
                                                               C.c_void_p(ps.data_ptr()), n, window, stride, n_win, h, w,
                                                               C.c_void_p(out.data_ptr()), 0, _lib.stream_ptr()))
     return out
+
+
+def sequence_tuples(cnt, seqn=2):
+    """Sliding `seqn`-tuples of consecutive count frames as a VIEW: [n_win, 2, H, W] -> [n_win - seqn + 1, seqn, 2, H, W]
+    (what `custom_collate` + `concat_dict` stack for batch 1, h5dataloader.py:293-330; no copy, no re-encoding)."""
+    n = cnt.shape[0] - seqn + 1
+    if n <= 0:
+        raise ValueError('need at least %d windows, got %d' % (seqn, cnt.shape[0]))
+    st = cnt.stride()
+    return cnt.as_strided((n, seqn) + tuple(cnt.shape[1:]), (st[0], st[0]) + tuple(st[1:]))
+
+
+def sequence_item(cnt, i, sequence_length, seqn=2, step_size=1):
+    """Item i of the reference's InferenceHDF5DataLoaderSequence for one recording (batch 1): the list of
+    `sequence_length - seqn + 1` dicts-worth of 'inp_cnt' tensors [1, seqn, 2, H, W] built from windows
+    [i*step_size, i*step_size + sequence_length) (SequenceDataset.__getitem__, h5dataset.py:666-700; custom_collate,
+    h5dataloader.py:293-317).  The inference loop reads element 0 (infer_BMCNet.py:48)."""
+    j = i * step_size
+    if j + sequence_length > cnt.shape[0]:
+        raise IndexError('item %d needs windows up to %d, the recording has %d' % (i, j + sequence_length, cnt.shape[0]))
+    t = sequence_tuples(cnt[j:j + sequence_length], seqn)
+    return [t[m:m + 1] for m in range(t.shape[0])]

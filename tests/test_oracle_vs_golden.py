@@ -150,3 +150,18 @@ def test_redistribute_oracle_exact_vs_reference(golden_dir):
     assert np.array_equal(R.event_redistribute(torch.from_numpy(d['nop_in']), False).numpy(), d['nop_out'])
     assert np.array_equal(R.event_redistribute(torch.zeros(2, 3, 4, 5), False).numpy(), d['zero_out'])
     assert np.array_equal(R.stack2cnt(torch.from_numpy(d['s2c_in'])).numpy(), d['s2c_out'])
+
+
+def test_sequence_tuples_are_views_of_consecutive_windows():
+    from bmcnet_esr_b200.dataloader.h5windows import sequence_item, sequence_tuples
+    cnt = torch.arange(7 * 2 * 3 * 4, dtype=torch.float32).view(7, 2, 3, 4)
+    t = sequence_tuples(cnt, 2)
+    assert tuple(t.shape) == (6, 2, 2, 3, 4) and t.data_ptr() == cnt.data_ptr()
+    for m in range(6):
+        assert torch.equal(t[m], torch.stack([cnt[m], cnt[m + 1]]))        # concat_dict: torch.stack(dim=1) at batch 1
+    item = sequence_item(cnt, 1, sequence_length=5, seqn=2, step_size=1)     # windows 1..5 -> 4 tuples
+    assert len(item) == 4 and tuple(item[0].shape) == (1, 2, 2, 3, 4)
+    assert torch.equal(item[0][0, 0], cnt[1]) and torch.equal(item[3][0, 1], cnt[5])
+    assert torch.equal(item[0].transpose(1, 2)[0, :, 1], cnt[2])            # input_stack = inp_cnt.transpose(1, 2), infer_BMCNet.py:50
+    with pytest.raises(IndexError):
+        sequence_item(cnt, 3, sequence_length=5)
