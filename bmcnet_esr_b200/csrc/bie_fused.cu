@@ -669,15 +669,17 @@ __global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// att_fold_tc: the same fold on the tensor core.  One CTA per (instance, image, k, block of 32 rows c):
-//   rows live in TMEM lanes 0..31 of M=128 MMAs (lanes 32..127 compute on don't-care rows).
+// att_fold_tc: the same fold on the tensor core.  One CTA per (instance, image, k): all 128 rows c are the M of the
+//   MMAs, warp w post-processes rows 32 w .. 32 w + 31 (its TMEM lane quarter).  (A CTA per 32-row block used a
+//   quarter of every MMA, loaded Wv four times and ran the softmax on one warp: 39.8 -> 35 us per launch at B=95,
+//   65 -> 49 us for the two-instance launches of BMCNet at B=76.)
 //   G is split into two fp16 terms (hi + lo, after an exact 2^-8 scaling that keeps sums of
 //   thousands of pixels inside the fp16 range), so  att = (G_hi + G_lo) Wv^T  keeps ~22 bits.
 //   MMA 1: att  = G_hi Wv^T + G_lo Wv^T      A = G tiles (K-major, K = i), B = Wv (K-major rows c')
 //   warp 0: + s bv^T, * scale, row softmax (three passes over TMEM), P -> fp16 tile, bias' = P bv
 //   MMA 2: M    = P Wv                        A = P (K-major, K = c'),    B = Wv as [K = c'][N = i] (N-major)
 //   warp 0: M -> fp16 chunk-major rows, 128 contiguous bytes per (row, chunk)
-constexpr int kFoldTcRows = 32;
+constexpr int kFoldTcRows = 128;
 constexpr int kFoldTcThreads = 128;
 constexpr int kFoldTcSmem = 3 * kTensBytes + 1024;     // Wv, G_hi (later P), G_lo
 constexpr float kGScale = 1.f / 256.f;
@@ -716,9 +718,10 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
         tma_load_2d(s_wv + kHalfBytes, &map_w, &bar_w, 0, row + 128);
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 256);
-    // G rows [32 rb, 32 rb + 32) summed over the partial slots (fixed order), split hi / lo, into tile rows 0..31
-    {
-        const float* __restrict__ gp = p.g_partial + (((long)slot_a * 2 + k) * 128 + rb * kFoldTcRows) * 128;
+    // G rows summed over the partial slots (fixed order), split hi / lo, into the tile rows; 32 rows at a time
+#pragma unroll 1
+    for (int r32 = 0; r32 < kFoldTcRows / 32; ++r32) {
+        const float* __restrict__ gp = p.g_partial + (((long)slot_a * 2 + k) * 128 + rb * kFoldTcRows + r32 * 32) * 128;
         float4 a[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) a[u] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -737,7 +740,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = tid + kFoldTcThreads * u, r = idx >> 5, i = (idx & 31) * 4;
+            const int idx = tid + kFoldTcThreads * u, r = r32 * 32 + (idx >> 5), i = (idx & 31) * 4;
             const float g[4] = {a[u].x * kGScale, a[u].y * kGScale, a[u].z * kGScale, a[u].w * kGScale};
             float h[4], l[4];
 #pragma unroll
@@ -777,17 +780,18 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
         umma_commit(&bar_mma);
     }
     float bsum = 0.f;
-    if (warp == 0) {
-        // rows 0..31 = TMEM lanes 0..31: only warp 0 may read them
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;      // warp w reads TMEM lanes 32 w .. 32 w + 31 = its rows
+    const int my_row = warp * 32 + lane;
+    {
         mbar_wait(&bar_mma, 0);
         tc_fence_after_sync();
-        const float sc = s_s[lane];
+        const float sc = s_s[my_row];
         const float k_att = p.scale / kGScale;         // undo the 2^-8 scaling of G together with nf^-0.5
         float mx = -INFINITY;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem + c * 32, v);
+            tmem_ld_32x32(tmem + lane_off + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale);
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem + c * 32, v);
+            tmem_ld_32x32(tmem + lane_off + c * 32, v);
             tmem_ld_wait();
 #pragma unroll
             for (int j = 0; j < 32; ++j) sum += expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx);
@@ -805,7 +809,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem + c * 32, v);
+            tmem_ld_32x32(tmem + lane_off + c * 32, v);
             tmem_ld_wait();
             float f[32];
 #pragma unroll
@@ -813,7 +817,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
                 f[j] = expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx) * inv;
                 bsum += f[j] * s_bv[c * 32 + j];
             }
-            store_tile_row32(s_gh, lane, c, f);        // P row (the first MMA group has retired: its tiles are free)
+            store_tile_row32(s_gh, my_row, c, f);      // P row (the first MMA group has retired: its tiles are free)
         }
         fence_proxy_async_smem();
         tc_fence_before_sync();
@@ -831,16 +835,16 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
                      s8 ? 1u : 0u);
         umma_commit(&bar_mma);
     }
-    if (warp == 0) {
+    {
         mbar_wait(&bar_mma, 1);
         tc_fence_after_sync();
         const int pair = inst * 2 + k;
-        const int c_row = rb * kFoldTcRows + lane;
+        const int c_row = rb * kFoldTcRows + my_row;
         act_t* mb = p.m_base + ((long)pair * p.B + b) * 256 * 64;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
-            tmem_ld_32x32(tmem + 128 + c * 32, v);
+            tmem_ld_32x32(tmem + 128 + lane_off + c * 32, v);
             tmem_ld_wait();
             // columns i = 32 c .. 32 c + 31 -> chunk c / 2, 64 contiguous bytes of row c_row
             uint4* dst = reinterpret_cast<uint4*>(mb + ((c >> 1) * 128 + c_row) * 64 + (c & 1) * 32);
