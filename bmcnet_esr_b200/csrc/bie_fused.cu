@@ -671,8 +671,9 @@ __global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
 // ---------------------------------------------------------------------------------------------
 // att_fold_tc: the same fold on the tensor core.  One CTA per (instance, image, k): all 128 rows c are the M of the
 //   MMAs, warp w post-processes rows 32 w .. 32 w + 31 (its TMEM lane quarter).  (A CTA per 32-row block used a
-//   quarter of every MMA, loaded Wv four times and ran the softmax on one warp: 39.8 -> 35 us per launch at B=95,
-//   65 -> 49 us for the two-instance launches of BMCNet at B=76.)
+//   quarter of every MMA, loaded Wv four times and ran the softmax on one warp.)  All 16 warps load G; the softmax is
+//   two TMEM sweeps (max; exp + store E unnormalised, the row sum scales M and the bias afterwards).
+//   Per launch at B=95: 39.8 -> 26.7 us; two-instance launches of BMCNet at B=76: 65 -> 39 us.
 //   G is split into two fp16 terms (hi + lo, after an exact 2^-8 scaling that keeps sums of
 //   thousands of pixels inside the fp16 range), so  att = (G_hi + G_lo) Wv^T  keeps ~22 bits.
 //   MMA 1: att  = G_hi Wv^T + G_lo Wv^T      A = G tiles (K-major, K = i), B = Wv (K-major rows c')
@@ -680,7 +681,7 @@ __global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
 //   MMA 2: M    = P Wv                        A = P (K-major, K = c'),    B = Wv as [K = c'][N = i] (N-major)
 //   warp 0: M -> fp16 chunk-major rows, 128 contiguous bytes per (row, chunk)
 constexpr int kFoldTcRows = 128;
-constexpr int kFoldTcThreads = 128;
+constexpr int kFoldTcThreads = 512;     // warps 0-3 own the TMEM lane quarters; all 16 warps load G (one 32-row block per 4 warps)
 constexpr int kFoldTcSmem = 3 * kTensBytes + 1024;     // Wv, G_hi (later P), G_lo
 constexpr float kGScale = 1.f / 256.f;
 
@@ -719,8 +720,8 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 256);
     // G rows summed over the partial slots (fixed order), split hi / lo, into the tile rows; 32 rows at a time
-#pragma unroll 1
-    for (int r32 = 0; r32 < kFoldTcRows / 32; ++r32) {
+    {
+        const int r32 = warp >> 2, ltid = tid & 127;       // 4 warps per 32-row block, all blocks in flight at once
         const float* __restrict__ gp = p.g_partial + (((long)slot_a * 2 + k) * 128 + rb * kFoldTcRows + r32 * 32) * 128;
         float4 a[8];
 #pragma unroll
@@ -731,7 +732,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
             for (int d = 0; d < 3; ++d)
 #pragma unroll
                 for (int u = 0; u < 8; ++u)
-                    t[d][u] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(gp + (long)(s + d) * 2 * 128 * 128 + (tid + kFoldTcThreads * u) * 4)
+                    t[d][u] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(gp + (long)(s + d) * 2 * 128 * 128 + (ltid + 128 * u) * 4)
                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int d = 0; d < 3; ++d)
@@ -740,7 +741,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
         }
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
-            const int idx = tid + kFoldTcThreads * u, r = r32 * 32 + (idx >> 5), i = (idx & 31) * 4;
+            const int idx = ltid + 128 * u, r = r32 * 32 + (idx >> 5), i = (idx & 31) * 4;
             const float g[4] = {a[u].x * kGScale, a[u].y * kGScale, a[u].z * kGScale, a[u].w * kGScale};
             float h[4], l[4];
 #pragma unroll
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
             *reinterpret_cast<uint2*>(tile_addr4(s_gl, r, i)) = make_uint2(pack_act2(l[0], l[1]), pack_act2(l[2], l[3]));
         }
     }
-    s_bv[tid] = (k == 0 ? p.bv[0] : p.bv[1])[tid];
+    if (tid < 128) s_bv[tid] = (k == 0 ? p.bv[0] : p.bv[1])[tid];
     if (tid < kFoldTcRows) {
         float sv = 0.f;
         const float* __restrict__ sp = p.s_partial + (long)slot_a * 256 + k * 128 + rb * kFoldTcRows + tid;
@@ -779,10 +780,10 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
                              (t | c | ks) ? 1u : 0u);
         umma_commit(&bar_mma);
     }
-    float bsum = 0.f;
+    float bsum = 0.f, inv = 1.f;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;      // warp w reads TMEM lanes 32 w .. 32 w + 31 = its rows
     const int my_row = warp * 32 + lane;
-    {
+    if (warp < 4) {
         mbar_wait(&bar_mma, 0);
         tc_fence_after_sync();
         const float sc = s_s[my_row];
@@ -796,16 +797,9 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
 #pragma unroll
             for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale);
         }
+        // one pass: E = exp(logit - max) goes to the tile UNnormalised (values in (0, 1]); the row sum is applied
+        // to M = E Wv and to the bias afterwards (same products, one TMEM sweep and 128 exponentials fewer)
         float sum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-            uint32_t v[32];
-            tmem_ld_32x32(tmem + lane_off + c * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) sum += expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx);
-        }
-        const float inv = 1.f / sum;
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
             uint32_t v[32];
@@ -814,11 +808,14 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-                f[j] = expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx) * inv;
+                f[j] = __expf(__uint_as_float(v[j]) * k_att + sc * s_bv[c * 32 + j] * p.scale - mx);
+                sum += f[j];
                 bsum += f[j] * s_bv[c * 32 + j];
             }
-            store_tile_row32(s_gh, my_row, c, f);      // P row (the first MMA group has retired: its tiles are free)
+            store_tile_row32(s_gh, my_row, c, f);      // E row (the first MMA group has retired: its tiles are free)
         }
+        inv = 1.f / sum;
+        bsum *= inv;
         fence_proxy_async_smem();
         tc_fence_before_sync();
     }
@@ -835,7 +832,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
                      s8 ? 1u : 0u);
         umma_commit(&bar_mma);
     }
-    {
+    if (warp < 4) {
         mbar_wait(&bar_mma, 1);
         tc_fence_after_sync();
         const int pair = inst * 2 + k;
@@ -850,10 +847,10 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
             uint4* dst = reinterpret_cast<uint4*>(mb + ((c >> 1) * 128 + c_row) * 64 + (c & 1) * 32);
 #pragma unroll
             for (int u = 0; u < 4; ++u)
-                dst[u] = make_uint4(pack_act2(__uint_as_float(v[u * 8]), __uint_as_float(v[u * 8 + 1])),
-                                    pack_act2(__uint_as_float(v[u * 8 + 2]), __uint_as_float(v[u * 8 + 3])),
-                                    pack_act2(__uint_as_float(v[u * 8 + 4]), __uint_as_float(v[u * 8 + 5])),
-                                    pack_act2(__uint_as_float(v[u * 8 + 6]), __uint_as_float(v[u * 8 + 7])));
+                dst[u] = make_uint4(pack_act2(__uint_as_float(v[u * 8]) * inv, __uint_as_float(v[u * 8 + 1]) * inv),
+                                    pack_act2(__uint_as_float(v[u * 8 + 2]) * inv, __uint_as_float(v[u * 8 + 3]) * inv),
+                                    pack_act2(__uint_as_float(v[u * 8 + 4]) * inv, __uint_as_float(v[u * 8 + 5]) * inv),
+                                    pack_act2(__uint_as_float(v[u * 8 + 6]) * inv, __uint_as_float(v[u * 8 + 7]) * inv));
         }
         p.bias_img[((long)pair * p.B + b) * 128 + c_row] = bsum;
         tc_fence_before_sync();
