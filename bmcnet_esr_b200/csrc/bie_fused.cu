@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     __shared__ uint64_t acc_full[3], epi_done[2];      // per accumulator (A, B): strict ping-pong MMA <-> epilogue; [2] = U phase (both issuers)
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_f[128], bias_c[128], bias_u[128], gam_s[128], bet_s[128];
-    __shared__ float ln_sum[2][128], ln_var[2][128];
+    __shared__ float ln_sum[2][2][128], ln_var[2][2][128];     // [pass A / B][column half][row]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tpi = p.tiles_per_img;
@@ -340,18 +340,25 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     v0[j] = __float_as_uint(x0); v1[j] = __float_as_uint(x1);
                     sum += x0 + x1;
                 }
-                ln_sum[ch][r] = sum;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float mu = (sum + ln_sum[ch ^ 1][r]) * (1.f / 128.f);
-                float var = 0.f;
+                // The two threads of a row (column halves, warps q and q + 4) merge their moments with ONE exchange:
+                // local mean / centred sum of squares over 64 channels each, then Chan's combination -- as accurate as
+                // the two global passes, one barrier fewer, and the barrier spans the two warps of a lane quarter only.
+                const float m_loc = sum * (1.f / 64.f);
+                float m2 = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const float d0 = __uint_as_float(v0[j]) - mu, d1 = __uint_as_float(v1[j]) - mu;
-                    var += d0 * d0 + d1 * d1;
+                    const float d0 = __uint_as_float(v0[j]) - m_loc, d1 = __uint_as_float(v1[j]) - m_loc;
+                    m2 += d0 * d0 + d1 * d1;
                 }
-                ln_var[ch][r] = var;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                const float rstd = 1.f / sqrtf((var + ln_var[ch ^ 1][r]) * (1.f / 128.f) + p.ln_eps);
+                ln_sum[a][ch][r] = sum;
+                ln_var[a][ch][r] = m2;
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+                const float sum_o = ln_sum[a][ch ^ 1][r], m2_o = ln_var[a][ch ^ 1][r];
+                const float mu = (sum + sum_o) * (1.f / 128.f);
+                const float da = m_loc - mu, db = sum_o * (1.f / 64.f) - mu;
+                const float var = m2 + m2_o + 64.f * (da * da + db * db);
+                const float rstd = rsqrtf(var * (1.f / 128.f) + p.ln_eps);
+                // (buffers alternate between the A and the B pass: the barrier of the next pass orders the reuse)
                 uint8_t* dst = a == 0 ? s_y : s_xs;
                 float f[32];
 #pragma unroll
