@@ -154,6 +154,16 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const void* map, uin
         : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async group); rows / columns outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // Pull a 2-D box into L2 only (no shared-memory destination, no barrier): used to start the HBM read
 // of a tile whose shared-memory buffer is still busy.
 __device__ __forceinline__ void tma_prefetch_l2_2d(const void* map, int c0, int c1) {

@@ -60,6 +60,8 @@ struct GemmJobDev {
     // conv_slab2_tc (gemm_slab2.cu): the same operands behind 32-channel / 64-byte-swizzle boxes,
     // indices into GemmParams::maps32 (valid when GemmParams::has32)
     signed char a_map32[kMaxSeg], t1_map32[kMaxSeg], w_map32;
+    signed char out_map32;     // maps32 index of the OUTPUT tensor behind [32 rows x 64 ch] SWIZZLE_128B boxes (TMA-store epilogue), or -1
+    int out_map_row;           // row of `out` inside that tensor
 };
 
 struct alignas(64) GemmParams {

@@ -16,9 +16,10 @@
 //    its epilogue overlaps the MMAs of the next phases, as before.
 //    L2 -> SM bytes per tile: 144 KB weights + 111 KB slabs = 255 KB (was 400 KB).
 //  * The epilogue drains its accumulator into registers first (the accumulator is needed again at
-//    once, by the tile after next) and stores straight from registers: a lane pair swaps halves so
-//    every lane holds two adjacent channels of one pixel, a warp store covers two 64-byte runs.  No
-//    shared-memory staging, no bank conflicts.
+//    once, by the tile after next), in the mma-fragment layout (tcgen05.ld.16x256b); the four warps of a
+//    128-pixel half assemble [32 px][128 ch] chunks in shared memory with stmatrix.trans (SWIZZLE_128B,
+//    conflict-free) and one thread TMA-stores each chunk: 256 contiguous bytes per pixel instead of four
+//    64-byte runs from four warps, no per-thread global stores (3x3 launch at B=95: 162 -> 156.5 us).
 //
 // Operand roles as in conv_slabt_tc: A = weight tile (M = 128 output channels), B = 256-pixel tap
 // view of the slab (N = 256), TMEM lane = output channel, column = pixel.  Same feature set: N = 128
@@ -38,7 +39,7 @@ constexpr int kN = 128;                               // output channels
 constexpr int kWBox = kN * kRowBytes;                 // one tap of one K step: 8 KB
 constexpr int kWGroup = 3;                            // taps per weight slot
 constexpr int kWSlot = kWGroup * kWBox;               // 24 KB
-constexpr int kWSlots = 4;
+constexpr int kWSlots = 3;
 constexpr int kSlabStages = 4;                        // two per accumulator / MMA issuer
 constexpr int kMaxSteps = 16;
 
@@ -68,7 +69,10 @@ struct Phase {
     int iw_slot, iw_par;            // weight ring position of the phase's first slot
 };
 
-template <int DBG>      // measurement builds (BMC_SLAB2_DBG): 1 = no operand movement (MMAs on stale shared memory), 2 = no epilogue stores
+// DBG selects the epilogue / measurement build (BMC_SLAB2_DBG): 32 = TMA-store epilogue (the product path whenever the
+// outputs sit behind a tensor map), 0 = register epilogue with 4-byte stores (fallback; forced by BMC_SLAB2_DBG=64),
+// 8 = stmatrix + 16-byte stores, 1 = no operand movement (MMAs on stale shared memory), 2 = no epilogue stores, 4 = store probe
+template <int DBG>
 __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
@@ -76,7 +80,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
     const int n_boxes = p.slab_boxes;
     const int slab_bytes = n_boxes * p.abox32_rows * kRowBytes;
     uint8_t* smem_w = smem + S * slab_bytes;
-    uint8_t* smem_stage = smem_w + kWSlots * kWSlot;               // 8 epilogue warps x 2 KB (stmatrix epilogue)
+    uint8_t* smem_stage = smem_w + kWSlots * kWSlot;               // 32 KB: stmatrix epilogues (8 warps x 2 KB, or [half][buffer][8 KB])
 
     __shared__ uint64_t a_full[S], a_empty[S], w_full[kWSlots], w_empty[kWSlots];
     __shared__ uint64_t acc_full[2], acc_empty[2];
@@ -301,6 +305,66 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
             mbar_wait(&acc_full[buf], (li >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t trow = tmem_base + buf * 256 + ph * 128 + ((uint32_t)(q * 32) << 16);
+            if (DBG & 32) {
+                // TMA-store epilogue: the four warps of a 128-pixel half assemble [32 px][128 ch] chunks in shared memory
+                // (fragment-layout TMEM reads, stmatrix.trans, SWIZZLE_128B) and one thread stores each chunk as two
+                // [32 x 64] boxes: 256 contiguous bytes per pixel, no per-thread global stores.  Two 8 KB buffers per half.
+                uint32_t f[4][2][16];
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) tmem_ld_16x256b_x4(trow + c * 32 + ((uint32_t)(hf * 16) << 16), f[c][hf]);
+                tmem_ld_wait();
+                tc_fence_before_sync();
+                if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                const int tr = lane >> 2, tc2 = (lane & 3) * 2;
+                float bia[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int chn = q * 32 + g * 8 + tr;
+                    bia[g] = (job.bias ? job.bias[chn] : 0.f) + (job.bias_img ? job.bias_img[img_h * kN + chn] : 0.f);
+                }
+                const bool store_half = px_base < rows_total;               // rows_total is a multiple of 128: a half is in or out
+                const bool leader = q == 0 && lane == 0;
+                const CUtensorMap* omap = &p.maps32[job.out_map32];
+                const int orow = job.out_map_row + (int)(job.out_row_base + px_base);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint8_t* sbuf = smem_stage + (ph * 2 + (c & 1)) * 8192;  // two boxes: channels 0-63, 64-127
+                    uint8_t* box = sbuf + (q >> 1) * 4096;
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t plo[4], phi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int col = 8 * k + tc2;
+                            const bool v0 = (valid[c] >> col) & 1u, v1 = (valid[c] >> (col + 1)) & 1u;
+                            float a0 = __uint_as_float(f[c][hf][4 * k]) + bia[2 * hf], a1 = __uint_as_float(f[c][hf][4 * k + 1]) + bia[2 * hf];
+                            float b0 = __uint_as_float(f[c][hf][4 * k + 2]) + bia[2 * hf + 1], b1 = __uint_as_float(f[c][hf][4 * k + 3]) + bia[2 * hf + 1];
+                            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
+                            plo[k] = pack_act2(v0 ? a0 : 0.f, v1 ? a1 : 0.f);
+                            phi[k] = pack_act2(v0 ? b0 : 0.f, v1 ? b1 : 0.f);
+                        }
+                        // lane l addresses pixel l (a 128-byte row of the box); 16-byte chunk = (q & 1) * 4 + channel octet, XOR row & 7
+                        const int c16 = (q & 1) * 4 + 2 * hf;
+                        stmatrix_x4_trans(box + lane * 128 + (((c16) ^ (lane & 7)) << 4), plo[0], plo[1], plo[2], plo[3]);
+                        stmatrix_x4_trans(box + lane * 128 + (((c16 + 1) ^ (lane & 7)) << 4), phi[0], phi[1], phi[2], phi[3]);
+                    }
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + ph) : "memory");
+                    if (leader) {
+                        if (store_half) {
+                            tma_store_2d(omap, sbuf, 0, orow + c * 32);
+                            tma_store_2d(omap, sbuf + 4096, 64, orow + c * 32);
+                        }
+                        tma_store_commit();
+                        tma_store_wait_read<1>();                             // the other buffer (chunk c - 1) has been read
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + ph) : "memory");
+                }
+                if (li + 1 == n_mine && leader) tma_store_wait_all();
+                continue;
+            }
             if (DBG & 8) {
                 // stmatrix epilogue: the accumulator is read in the mma-fragment layout (16 lanes x 8 columns per
                 // repetition), packed to 16 bits and written TRANSPOSED into a [32 px][32 ch] staging tile with four
@@ -419,7 +483,7 @@ static int slab2_boxes(const Geom& g, int n_taps) {
 }
 
 static int slab2_smem(const Geom& g, int n_taps) {
-    return kSlabStages * slab2_boxes(g, n_taps) * slab2_box_rows(g, n_taps) * kRowBytes + kWSlots * kWSlot + 8 * 2048 + 1024;
+    return kSlabStages * slab2_boxes(g, n_taps) * slab2_box_rows(g, n_taps) * kRowBytes + kWSlots * kWSlot + 32 * 1024 + 1024;
 }
 
 bool slab2_supported(const GemmParams& p) {
@@ -476,6 +540,7 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
     }
     int grid = p.n_full < sm_count() ? p.n_full : sm_count();
@@ -486,12 +551,16 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
     }
     static int dbg = -1;
     if (dbg < 0) { const char* e = getenv("BMC_SLAB2_DBG"); dbg = e ? atoi(e) : 0; }
+    bool tma_out = true;
+    for (int j = 0; j < p.n_jobs; ++j) tma_out = tma_out && p.jobs[j].out_map32 >= 0;
     if (dbg == 1) conv_slab2_tc<1><<<grid, kThreads2, smem, st>>>(p);
     else if (dbg == 2) conv_slab2_tc<2><<<grid, kThreads2, smem, st>>>(p);
     else if (dbg == 3) conv_slab2_tc<3><<<grid, kThreads2, smem, st>>>(p);
     else if (dbg == 4) conv_slab2_tc<4><<<grid, kThreads2, smem, st>>>(p);
     else if (dbg == 8) conv_slab2_tc<8><<<grid, kThreads2, smem, st>>>(p);
-    else conv_slab2_tc<0><<<grid, kThreads2, smem, st>>>(p);
+    else if (dbg == 32 && tma_out) conv_slab2_tc<32><<<grid, kThreads2, smem, st>>>(p);
+    else if (dbg == 0 && tma_out) conv_slab2_tc<32><<<grid, kThreads2, smem, st>>>(p);     // product path: TMA-store epilogue
+    else conv_slab2_tc<0><<<grid, kThreads2, smem, st>>>(p);                               // outputs without a tensor map / BMC_SLAB2_DBG=64
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

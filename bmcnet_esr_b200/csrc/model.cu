@@ -169,6 +169,7 @@ struct bmc_model {
     char* ws = nullptr;
     CUtensorMap map_act, map_att, map_slab, map_mi, map_mi64, map_w128, map_w64, map_w32, map_p;
     CUtensorMap map_act_s64, map_mi_s64, map_w_s64, map_p_s64;   // 32-channel / 64-byte-swizzle boxes (conv_slab2_tc)
+    CUtensorMap map_act_out;               // activation arena behind [32 rows x 64 ch] boxes (TMA-store epilogue)
     int abox = 64;                         // rows per TMA box of map_slab / map_mi64 (slab_box_rows)
     int abox32 = 64;                       // rows per TMA box of map_act_s64 / map_mi_s64 (slab2_box_rows)
     // plan
@@ -311,6 +312,7 @@ struct Builder {
         p.maps[6] = m->map_w64;
         p.maps[7] = m->map_att;                 // act arena, 64-row boxes (1x1 launches of the unfused plan)
         p.maps32[0] = m->map_act_s64; p.maps32[1] = m->map_mi_s64; p.maps32[2] = m->map_w_s64; p.maps32[3] = m->map_p_s64;
+        p.maps32[4] = m->map_act_out;
         p.has32 = taps == 9; p.abox32_rows = m->abox32;
         p.n_jobs = (int)jobs.size();
         const int n_plain = (int)jobs[0].segs.size();
@@ -359,6 +361,8 @@ struct Builder {
             d.res_row_base = 0;
             d.out = js.out_slot >= 0 ? m->slot_ptr(js.out_slot) : nullptr;
             d.out_row_base = 0;
+            d.out_map32 = js.out_slot >= 0 ? 4 : -1;
+            d.out_map_row = js.out_slot >= 0 ? (int)(js.out_slot * g.rows()) : 0;
             d.out_f32 = js.out_f32 ? m->a32_ptr() : nullptr;
             if (js.ln >= 0) {
                 d.ln_gamma = m->f32_dev + m->lns[js.ln].gamma_off;
@@ -921,6 +925,7 @@ extern "C" BMC_EXPORT int bmc_model_bind_workspace(bmc_model_t* m, void* workspa
     if (!rc) rc = make_tmap_2d_act_sw64(&m->map_act_s64, m->slot_ptr(0), rows * m->n_slots, 128, (uint32_t)m->abox32);
     if (!rc) rc = make_tmap_2d_act_sw64(&m->map_mi_s64, m->mi_ptr(), rows, 64, (uint32_t)m->abox32);
     if (!rc) rc = make_tmap_2d_act_sw64(&m->map_p_s64, m->p_ptr(), (uint64_t)kMaxPairs * m->g.B * 256, 64, 128);
+    if (!rc) rc = make_tmap_2d_act(&m->map_act_out, m->slot_ptr(0), rows * m->n_slots, 128, 32, 64);
     if (rc) return rc;
     m->dry = false;
     Builder b{m};
@@ -1116,6 +1121,23 @@ extern "C" BMC_EXPORT int bmc_conv_gemm(const bmc_gemm_job_t* jobs, int n_jobs, 
             }
         }
         p.has32 = ok ? 1 : 0;
+        // output tensors behind [32 x 64] boxes for the TMA-store epilogue (rows: what this call may write)
+        for (int j = 0; j < n_jobs; ++j) { p.jobs[j].out_map32 = -1; p.jobs[j].out_map_row = 0; }
+        for (int j = 0; j < n_jobs && ok; ++j) {
+            if (!jobs[j].out_act16) continue;
+            uint64_t rows = 0;
+            for (int i = 0; i < n_jobs; ++i)
+                if (jobs[i].out_act16 == jobs[j].out_act16) rows = std::max<uint64_t>(rows, (uint64_t)jobs[i].out_row_base + (uint64_t)g.rows());
+            int found = -1;
+            for (int i = 0; i < j; ++i)
+                if (jobs[i].out_act16 == jobs[j].out_act16) found = p.jobs[i].out_map32;
+            if (found < 0 && n32 < kMaxMaps32) {
+                int rc = make_tmap_2d_act(&p.maps32[n32], jobs[j].out_act16, rows, 128, 32, 64);
+                if (rc) return rc;
+                found = n32++;
+            }
+            p.jobs[j].out_map32 = (signed char)found;
+        }
     }
     return launch_conv_gemm(p, impl, as_stream(stream));
 }
