@@ -11,9 +11,10 @@
 //
 // Accumulator: TMEM lane = output channel, column = pixel of the tile (2 x 256 columns, double
 // buffered).  The epilogue therefore owns a CHANNEL per thread and 32 consecutive pixels per
-// tcgen05.ld; bias is a per-thread scalar, the halo mask a per-column bit; lane pairs swap halves so that
-// every lane stores two adjacent channels of one pixel (a warp store covers two 64-byte runs) -- the
-// shared-memory transposition this replaced cost 128 KB of staging traffic per tile (mix launch 141 -> 135 us).
+// tcgen05.ld.  Outputs behind a tensor map (the model's arena) leave through the TMA-store epilogue of
+// conv_slab2_tc (fragment-layout reads, stmatrix.trans, one bulk store per [32 px][128 ch] chunk; mix launch at
+// B=95: 217 -> 209 us); otherwise lane pairs swap halves so that every lane stores two adjacent channels of one
+// pixel (a warp store covers two 64-byte runs).
 // Supported: N = 128 outputs, 16-bit output only, no epilogue residual / LayerNorm / fp32 side output
 // (the fused plan needs none of them: residuals are identity K segments); everything else falls back
 // to conv_slab_tc.  K steps, slab views, weight stages and the tile schedule are those of gemm_slab.cu.
@@ -34,12 +35,13 @@ constexpr int kN = 128;                               // output channels
 constexpr int kWBytes = kN * kChunkK * 2;             // one tap of one K chunk: 16 KB
 constexpr int kWStageBytes = kWGroup * kWBytes;
 
+template <bool TMA_OUT>     // outputs behind a tensor map: TMA-store epilogue (as conv_slab2_tc), else 4-byte stores from registers
 __global__ void __launch_bounds__(kThreadsT, 1) conv_slabt_tc(const __grid_constant__ GemmParams p) {
     extern __shared__ __align__(1024) uint8_t smem_dyn[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
     const int slab_bytes = p.slab_boxes * kBoxBytes;
     uint8_t* smem_w = smem + kSlabStages * slab_bytes;
-    uint8_t* smem_stage = smem_w + kWStages * kWStageBytes;      // 8 epilogue warps x 2 KB
+    uint8_t* smem_stage = smem_w + kWStages * kWStageBytes;      // 2 halves x 8 KB: [32 px][128 ch] chunks for the TMA store
 
     __shared__ uint64_t a_full[kSlabStages], a_empty[kSlabStages], w_full[kWStages], w_empty[kWStages];
     __shared__ uint64_t acc_full[2], acc_empty[2];
@@ -247,6 +249,72 @@ __global__ void __launch_bounds__(kThreadsT, 1) conv_slabt_tc(const __grid_const
             mbar_wait(&acc_full[buf], (lt >> 1) & 1);
             tc_fence_after_sync();
             const uint32_t trow = tmem_base + buf * 256 + ph * 128 + ((uint32_t)(q * 32) << 16);
+            if (TMA_OUT) {
+                // The four warps of a 128-pixel half assemble each [32 px][128 ch] chunk in shared memory (fragment-layout
+                // TMEM reads, stmatrix.trans, SWIZZLE_128B) and one thread stores it as two [32 x 64] boxes.  One 8 KB
+                // buffer per half: the next chunk waits until the store has read it (the accumulators are double
+                // buffered, so this epilogue only has to keep up with the MMAs of the next tile).
+                const long px_base = m0l + ph * 128;
+                const int tr = lane >> 2, tc2 = (lane & 3) * 2;
+                float bia[4];
+#pragma unroll
+                for (int g = 0; g < 4; ++g) bia[g] = bias_s[ph][q * 32 + g * 8 + tr];
+                const bool store_half = px_base < rows_total;               // rows_total is a multiple of 128
+                const bool leader = q == 0 && lane == 0;
+                const CUtensorMap* omap = &p.maps32[job.out_map32];
+                const int orow = job.out_map_row + (int)(job.out_row_base + px_base);
+                uint8_t* sbuf = smem_stage + ph * 8192;
+                uint8_t* box = sbuf + (q >> 1) * 4096;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t f[2][16];
+                    tmem_ld_16x256b_x4(trow + c * 32, f[0]);
+                    tmem_ld_16x256b_x4(trow + c * 32 + (16u << 16), f[1]);
+                    tmem_ld_wait();
+                    if (c == 3) {
+                        tc_fence_before_sync();
+                        if (lane == 0) mbar_arrive(&acc_empty[buf]);
+                    }
+                    unsigned valid_mask;
+                    {
+                        const long m = px_base + c * 32 + lane;
+                        const int img = (int)(m / p.g.R);
+                        const int r_img = (int)(m - (long)img * p.g.R);
+                        int y, x;
+                        valid_mask = __ballot_sync(0xffffffffu, m < rows_total && p.g.interior(r_img, y, x));
+                    }
+#pragma unroll
+                    for (int hf = 0; hf < 2; ++hf) {
+                        uint32_t plo[4], phi[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const int col = 8 * k + tc2;
+                            const bool v0 = (valid_mask >> col) & 1u, v1 = (valid_mask >> (col + 1)) & 1u;
+                            float a0 = __uint_as_float(f[hf][4 * k]) + bia[2 * hf], a1 = __uint_as_float(f[hf][4 * k + 1]) + bia[2 * hf];
+                            float b0 = __uint_as_float(f[hf][4 * k + 2]) + bia[2 * hf + 1], b1 = __uint_as_float(f[hf][4 * k + 3]) + bia[2 * hf + 1];
+                            if (relu) { a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); b0 = fmaxf(b0, 0.f); b1 = fmaxf(b1, 0.f); }
+                            plo[k] = pack_act2(v0 ? a0 : 0.f, v1 ? a1 : 0.f);
+                            phi[k] = pack_act2(v0 ? b0 : 0.f, v1 ? b1 : 0.f);
+                        }
+                        const int c16 = (q & 1) * 4 + 2 * hf;
+                        stmatrix_x4_trans(box + lane * 128 + (((c16) ^ (lane & 7)) << 4), plo[0], plo[1], plo[2], plo[3]);
+                        stmatrix_x4_trans(box + lane * 128 + (((c16 + 1) ^ (lane & 7)) << 4), phi[0], phi[1], phi[2], phi[3]);
+                    }
+                    fence_proxy_async_smem();
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + ph) : "memory");
+                    if (leader) {
+                        if (store_half) {
+                            tma_store_2d(omap, sbuf, 0, orow + c * 32);
+                            tma_store_2d(omap, sbuf + 4096, 64, orow + c * 32);
+                        }
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(3 + ph) : "memory");
+                }
+                if (li + 1 == n_mine && leader) tma_store_wait_all();
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 const long px0 = m0l + ph * 128 + c * 32;              // first pixel row of this chunk
@@ -326,8 +394,16 @@ int launch_conv_slabt(GemmParams p, cudaStream_t st) {
     const int smem = slabt_smem(p.slab_boxes);
     static int configured = 0;
     if (configured < smem) {
-        BMC_CUDA(cudaFuncSetAttribute(conv_slabt_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slabt_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slabt_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
+    }
+    bool tma_out = true;
+    for (int j = 0; j < p.n_jobs; ++j) tma_out = tma_out && p.jobs[j].out_map32 >= 0;
+    {
+        static int direct = -1;        // BMC_SLABT_DIRECT=1: force the register epilogue (measurement)
+        if (direct < 0) { const char* e = getenv("BMC_SLABT_DIRECT"); direct = e ? atoi(e) : 0; }
+        if (direct) tma_out = false;
     }
     int grid = p.n_full < sm_count() ? p.n_full : sm_count();
     {   // measurement switch: fewer CTAs -> is a tile's time set by the SM or by the shared L2 fabric?
@@ -335,7 +411,8 @@ int launch_conv_slabt(GemmParams p, cudaStream_t st) {
         if (cap < 0) { const char* e = getenv("BMC_SLABT_GRID"); cap = e ? atoi(e) : 0; }
         if (cap > 0 && grid > cap) grid = cap;
     }
-    conv_slabt_tc<<<grid, kThreadsT, smem, st>>>(p);
+    if (tma_out) conv_slabt_tc<true><<<grid, kThreadsT, smem, st>>>(p);
+    else conv_slabt_tc<false><<<grid, kThreadsT, smem, st>>>(p);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
