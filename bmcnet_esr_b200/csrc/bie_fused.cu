@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
     const int B = p.g.B, R = p.g.R;
+    pdl_wait();                  // only static weights were read so far; activations of the previous kernel from here on
+    pdl_launch_dependents();     // the next kernel may take over SMs as CTAs of this one exit (it waits for this grid itself)
 
     if (warp == 0) {
         // ------------------------------------------------------------ input tiles (lane l issues box l of the six)
@@ -726,6 +728,8 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
         tma_load_2d(s_wv + kHalfBytes, &map_w, &bar_w, 0, row + 128);
     }
     if (warp == 1) tmem_alloc(&tmem_base_s, 256);
+    pdl_wait();                  // Wv is static; the partial sums below come from the previous kernel
+    pdl_launch_dependents();     // the next kernel may take over SMs as CTAs of this one exit (it waits for this grid itself)
     // G rows summed over the partial slots (fixed order), split hi / lo, into the tile rows; 32 rows at a time
     {
         const int r32 = warp >> 2, ltid = tid & 127;       // 4 warps per 32-row block, all blocks in flight at once
@@ -905,7 +909,7 @@ int launch_bie_front(const BieFrontParams& p, cudaStream_t st) {
     }
     BieFrontParams q = p;
     q.prof = prof;
-    bie_front_tc<<<grid, kFrontThreads, kFrontSmem, st>>>(q);
+    BMC_CUDA(launch_pdl(bie_front_tc, dim3(grid), dim3(kFrontThreads), (size_t)kFrontSmem, st, q));
     BMC_CUDA(cudaGetLastError());
     if (prof && dumped++ == 7) {           // a warm launch
         cudaStreamSynchronize(st);
@@ -926,7 +930,7 @@ int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream
         BMC_CUDA(cudaFuncSetAttribute(att_fold_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldTcSmem));
         configured = true;
     }
-    att_fold_tc<<<p.n_inst * p.B * 2 * (128 / kFoldTcRows), kFoldTcThreads, kFoldTcSmem, st>>>(p, map_w);
+    BMC_CUDA(launch_pdl(att_fold_tc, dim3(p.n_inst * p.B * 2 * (128 / kFoldTcRows)), dim3(kFoldTcThreads), (size_t)kFoldTcSmem, st, p, map_w));
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

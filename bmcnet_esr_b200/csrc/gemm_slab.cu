@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(kThreadsSlab, 1) conv_slab_tc(const __grid_con
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();                  // the prologue above overlaps the previous kernel's tail; no global access before this point
+    pdl_launch_dependents();     // the next kernel may take over SMs as CTAs of this one exit (it waits for this grid itself)
 
     if (warp == 8) {
         // ------------------------------------------------------------ activation slabs
@@ -366,7 +368,7 @@ int launch_slab_n(const GemmParams& p, cudaStream_t st) {
     }
     const int total = p.n_full + p.n_half;
     const int grid = total < sm_count() ? total : sm_count();
-    kern<<<grid, kThreadsSlab, smem, st>>>(p);
+    BMC_CUDA(launch_pdl(kern, dim3(grid), dim3(kThreadsSlab), (size_t)smem, st, p));
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();                  // everything above overlaps the previous kernel's tail; no global access before this point
+    pdl_launch_dependents();     // the next kernel may take over SMs as CTAs of this one exit (it waits for this grid itself)
 
     if (warp == 8) {
         // ------------------------------------------------------------ activation slabs: per phase the older tile's, then the newer's
@@ -553,14 +555,14 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
     if (dbg < 0) { const char* e = getenv("BMC_SLAB2_DBG"); dbg = e ? atoi(e) : 0; }
     bool tma_out = true;
     for (int j = 0; j < p.n_jobs; ++j) tma_out = tma_out && p.jobs[j].out_map32 >= 0;
-    if (dbg == 1) conv_slab2_tc<1><<<grid, kThreads2, smem, st>>>(p);
-    else if (dbg == 2) conv_slab2_tc<2><<<grid, kThreads2, smem, st>>>(p);
-    else if (dbg == 3) conv_slab2_tc<3><<<grid, kThreads2, smem, st>>>(p);
-    else if (dbg == 4) conv_slab2_tc<4><<<grid, kThreads2, smem, st>>>(p);
-    else if (dbg == 8) conv_slab2_tc<8><<<grid, kThreads2, smem, st>>>(p);
-    else if (dbg == 32 && tma_out) conv_slab2_tc<32><<<grid, kThreads2, smem, st>>>(p);
-    else if (dbg == 0 && tma_out) conv_slab2_tc<32><<<grid, kThreads2, smem, st>>>(p);     // product path: TMA-store epilogue
-    else conv_slab2_tc<0><<<grid, kThreads2, smem, st>>>(p);                               // outputs without a tensor map / BMC_SLAB2_DBG=64
+    if (dbg == 1) BMC_CUDA(launch_pdl(conv_slab2_tc<1>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
+    else if (dbg == 2) BMC_CUDA(launch_pdl(conv_slab2_tc<2>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
+    else if (dbg == 3) BMC_CUDA(launch_pdl(conv_slab2_tc<3>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
+    else if (dbg == 4) BMC_CUDA(launch_pdl(conv_slab2_tc<4>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
+    else if (dbg == 8) BMC_CUDA(launch_pdl(conv_slab2_tc<8>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
+    else if (dbg == 32 && tma_out) BMC_CUDA(launch_pdl(conv_slab2_tc<32>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
+    else if (dbg == 0 && tma_out) BMC_CUDA(launch_pdl(conv_slab2_tc<32>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));     // product path: TMA-store epilogue
+    else BMC_CUDA(launch_pdl(conv_slab2_tc<0>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));                               // outputs without a tensor map / BMC_SLAB2_DBG=64
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

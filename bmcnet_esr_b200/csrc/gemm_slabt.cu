@@ -88,6 +88,8 @@ __global__ void __launch_bounds__(kThreadsT, 1) conv_slabt_tc(const __grid_const
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tmem_base = tmem_base_s;
+    pdl_wait();                  // the prologue above overlaps the previous kernel's tail; no global access before this point
+    pdl_launch_dependents();     // the next kernel may take over SMs as CTAs of this one exit (it waits for this grid itself)
 
     if (warp == 8) {
         // ------------------------------------------------------------ activation slabs (lane b issues box b)
@@ -411,8 +413,8 @@ int launch_conv_slabt(GemmParams p, cudaStream_t st) {
         if (cap < 0) { const char* e = getenv("BMC_SLABT_GRID"); cap = e ? atoi(e) : 0; }
         if (cap > 0 && grid > cap) grid = cap;
     }
-    if (tma_out) conv_slabt_tc<true><<<grid, kThreadsT, smem, st>>>(p);
-    else conv_slabt_tc<false><<<grid, kThreadsT, smem, st>>>(p);
+    if (tma_out) BMC_CUDA(launch_pdl(conv_slabt_tc<true>, dim3(grid), dim3(kThreadsT), (size_t)smem, st, p));
+    else BMC_CUDA(launch_pdl(conv_slabt_tc<false>, dim3(grid), dim3(kThreadsT), (size_t)smem, st, p));
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

@@ -1,5 +1,6 @@
 // Error plumbing, device queries and TMA descriptor encoding for libbmc_b200.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -17,6 +18,12 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
     set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
     return BMC_ERR_CUDA;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("BMC_PDL"); on = e ? atoi(e) : 0; }
+    return on != 0;
 }
 
 int sm_count() {
