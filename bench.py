@@ -47,10 +47,10 @@ WORKLOADS = {
 }
 CONV_MAC_PER_PX = 147456          # 3x3 128->128
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_ncu_full_*.txt):
-# conv_slab2_tc, 2 jobs, 45x80: B=95: 193.5 + 146.4 MB (algorithmic 193.0 read + 193.0 written; part of the output is
+# conv_slab2_tc, 2 jobs, 45x80: B=95: 193.4 + 143.0 MB (algorithmic 193.0 read + 193.0 written; part of the output is
 # still dirty in L2 when the kernel ends), B=57: 116.2 + 70.5 MB; encoders: bytes per event at 1e8 events
 # (12.04 / 16.04 for 12 / 16 algorithmic)
-NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): 339.9e6, ('plain', 57, 45, 80): 186.7e6}
+NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): 336.4e6, ('plain', 57, 45, 80): 186.7e6}
 NCU_ENC_BYTES_PER_EVENT, NCU_VOX_BYTES_PER_EVENT = 12.045, 16.035
 FLOP_PER_PX = {'plain': 9721856, 'full': 41574912}      # SURVEY 8d / BASELINE.md section 3
 
