@@ -424,6 +424,7 @@ def main():
         'roofline_encoder': {'kernel': 'scatter_kernel<ChannelsOp> (events_to_channels, %.0e events, %dx%d)' % (n_big, h, w),
                              'bound': 'hbm', 'achieved': enc_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': enc_gbs / hbm,
                              'traffic': NCU_ENC_BYTES_PER_EVENT * n_big if (h, w) == (45, 80) else None,
+                             'note': 'a read-only stream: it can exceed the peak, which is a copy (read + write) bandwidth',
                              'mevents_per_s': n_big / (enc_ms * 1e-3) / 1e6},
         'roofline_voxel': {'kernel': 'scatter_kernel<VoxelOp> (events_to_voxel, 5 bins, %.0e events, %dx%d)' % (n_vox, h, w),
                            'bound': 'hbm', 'achieved': vox_gbs, 'peak': hbm, 'unit': 'GB/s', 'frac': vox_gbs / hbm,
