@@ -35,6 +35,7 @@ SIGNATURES = {
     'bmc_encode_image': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_voxel': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_stack': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
+    'bmc_encode_stack_shard': (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_model_create': (_vp, [_i, _i, _i, _i, _i]),
     'bmc_model_destroy': (None, [_vp]),
     'bmc_model_weight_bytes': (_sz, [_vp]),

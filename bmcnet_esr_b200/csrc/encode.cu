@@ -373,8 +373,9 @@ __global__ void finalize_kernel(const int* __restrict__ cnt, const float* __rest
 // Bin boundaries of the stack encoders, evaluated exactly like encodings.py:172-178 + :75-97
 // (float32, two roundings for ts[0] + delta_t*bi, any-equal binary search).  One thread per
 // (bin, side); ~3 log2(n) dependent loads each.
+// `shift` re-bases the boundaries for a rank that holds events [shift, shift + n_local) of the recording.
 __global__ void bin_bounds_kernel(const float* __restrict__ ts, long n, int bins, long* beg,
-                                  long* end) {
+                                  long* end, long shift) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 2 * bins) return;
     const int bi = k >> 1;
@@ -395,7 +396,7 @@ __global__ void bin_bounds_kernel(const float* __restrict__ ts, long n, int bins
         if (mv < x) l = mid + 1; else r = mid - 1;
     }
     if (!found) res = right ? r : l;
-    if (right) end[bi] = res + 1; else beg[bi] = res;
+    if (right) end[bi] = res + 1 - shift; else beg[bi] = res - shift;
 }
 
 // One CTA per window (dataloader pattern: ~2048 events -> one [2,H,W] grid).  fp32 smem bins:
@@ -682,22 +683,33 @@ extern "C" BMC_EXPORT int bmc_encode_voxel(float* xs, float* ys, const float* ts
     return run_scatter(op, n, (long)bins * H * W, out, workspace, workspace_bytes, as_stream(stream));
 }
 
-extern "C" BMC_EXPORT int bmc_encode_stack(float* xs, float* ys, const float* ts, float* ps, int64_t n,
-                                int bins, int H, int W, int polarity, float* out, void* workspace,
-                                size_t workspace_bytes, unsigned flags, void* stream) {
-    int rc = check_common(xs, ys, ps, n, H, W, out);
+extern "C" BMC_EXPORT int bmc_encode_stack_shard(float* xs, float* ys, float* ps, int64_t n_local,
+                                const float* ts_all, int64_t n_total, int64_t first, int bins, int H, int W,
+                                int polarity, float* out, void* workspace, size_t workspace_bytes,
+                                unsigned flags, void* stream) {
+    int rc = check_common(xs, ys, ps, n_local, H, W, out);
     if (rc) return rc;
     BMC_REQUIRE(bins >= 1 && bins <= 64, "encode_stack: bins must be in [1,64], got %d", bins);
-    BMC_REQUIRE(n > 3 && ts, "encode_stack: n <= 3 is the reference's early-out (caller returns zeros)");
+    BMC_REQUIRE(n_total > 3 && ts_all, "encode_stack: n <= 3 is the reference's early-out (caller returns zeros)");
+    BMC_REQUIRE(first >= 0 && first + n_local <= n_total, "encode_stack_shard: events [%ld, %ld) outside [0, %ld)",
+                (long)first, (long)(first + n_local), (long)n_total);
     const long elems = (long)(polarity ? 2 : 1) * bins * H * W;
     Ws w;
     rc = carve(workspace, workspace_bytes, elems, w);
     if (rc) return rc;
-    bin_bounds_kernel<<<1, 128, 0, as_stream(stream)>>>(ts, n, bins, w.beg, w.end);
+    bin_bounds_kernel<<<1, 128, 0, as_stream(stream)>>>(ts_all, n_total, bins, w.beg, w.end, first);
     BMC_CUDA(cudaGetLastError());
     StackOp op;
-    op.xs = xs; op.ys = ys; op.ts = ts; op.ps = ps;
+    op.xs = xs; op.ys = ys; op.ts = nullptr; op.ps = ps;
     op.H = H; op.W = W; op.bins = bins; op.flags = flags & ~BMC_ENC_FLIP_Y;
     op.beg = w.beg; op.end = w.end; op.polarity = polarity;
-    return run_scatter(op, n, elems, out, workspace, workspace_bytes, as_stream(stream));
+    return run_scatter(op, n_local, elems, out, workspace, workspace_bytes, as_stream(stream));
+}
+
+extern "C" BMC_EXPORT int bmc_encode_stack(float* xs, float* ys, const float* ts, float* ps, int64_t n,
+                                int bins, int H, int W, int polarity, float* out, void* workspace,
+                                size_t workspace_bytes, unsigned flags, void* stream) {
+    BMC_REQUIRE(n > 3 && ts, "encode_stack: n <= 3 is the reference's early-out (caller returns zeros)");
+    return bmc_encode_stack_shard(xs, ys, ps, n, ts, n, 0, bins, H, W, polarity, out, workspace, workspace_bytes,
+                                  flags, stream);
 }

@@ -20,3 +20,80 @@ def frames_total(frames_per_rank, group=None):
             t = t.cuda()
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return int(t.item())
+
+
+# ---------------------------------------------------------------------------------------------------------
+# One recording encoded by several GPUs (SURVEY.md 8e, "one giant grid").  The encodings are sums over
+# events, so rank r encodes the contiguous range event_range(n, r, world) into a partial grid and ONE
+# all-reduce (NCCL over NVLink on the GPUs; 28.8 KB .. 9.2 MB against gigabytes of events) adds them.
+# Counts and stacks are integer-valued floats below 2^24, so the sum is exact in any order and the result is
+# bit-identical to the single-GPU encoder; voxel weights are fp32 partial sums (same 1e-6 relative bound).
+# ---------------------------------------------------------------------------------------------------------
+
+def event_range(n_events, rank, world, align=4):
+    """[lo, hi) of the events rank `rank` encodes: contiguous, near-equal, covering [0, n) exactly once; interior
+    cuts fall on multiples of `align` events so every rank's slice keeps the 16-byte alignment of the
+    vectorised loads."""
+    if not (0 <= rank < world):
+        raise ValueError('rank %d outside world of %d' % (rank, world))
+
+    def cut(r):
+        if r >= world:
+            return n_events
+        return min(n_events, (n_events * r // world) // align * align)
+    return cut(rank), cut(rank + 1)
+
+
+def sum_grids(grid, group=None):
+    """In-place sum of the ranks' partial grids (the path's only exchange step); identity without a process
+    group."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grid, op=dist.ReduceOp.SUM, group=group)
+    return grid
+
+
+def events_to_channels_sharded(xs, ys, ps, sensor_size=(180, 240), group=None):
+    """events_to_channels (reference encodings.py:290-305) of a recording split across ranks: pass this rank's
+    slice; every rank gets the full [2,H,W] counts."""
+    from .dataloader.encodings import events_to_channels
+    return sum_grids(events_to_channels(xs, ys, ps, sensor_size=sensor_size), group)
+
+
+def events_to_voxel_sharded(xs, ys, ts, ps, num_bins, sensor_size=(180, 240), group=None):
+    """events_to_voxel (reference encodings.py:272-287) of a split recording; ts is already normalised over the
+    WHOLE recording (base_dataset.py:30), so an event's bin weights do not depend on the split."""
+    from .dataloader.encodings import events_to_voxel
+    return sum_grids(events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=sensor_size), group)
+
+
+def _stack_sharded(xs, ys, ts_all, ps, first, B, sensor_size, polarity, group):
+    import torch
+    from . import _lib
+    from .dataloader import encodings as E
+    n_local = E._chk(xs, ys, ps)
+    E._chk(ts_all)
+    n_total = len(ts_all)
+    if first < 0 or first + n_local > n_total:
+        raise _lib.BmcError('events [%d, %d) outside the recording of %d' % (first, first + n_local, n_total))
+    eo = E._early_out(ts_all, B, sensor_size, xs.device)       # a property of the whole recording: same on all ranks
+    if eo is not None:
+        return eo
+    h, w = sensor_size
+    out = torch.empty(*((2, B, h, w) if polarity else (B, h, w)), dtype=torch.float32, device=xs.device)
+    E._run(lambda *a: _lib.lib().bmc_encode_stack_shard(E._p(xs), E._p(ys), E._p(ps), n_local, E._p(ts_all), n_total,
+                                                        int(first), B, h, w, int(polarity), *a, E._MUT,
+                                                        _lib.stream_ptr()), out)
+    return sum_grids(out, group)
+
+
+def events_to_stack_polarity_sharded(xs, ys, ts_all, ps, first, B, sensor_size=(180, 240), group=None):
+    """events_to_stack_polarity (reference encodings.py:151-199) of a split recording.  xs, ys, ps: this rank's
+    events [first, first + len(xs)); ts_all: the timestamps of the WHOLE recording (the bin boundaries and the
+    any-equal binary search of encodings.py:75-97 are evaluated on it by every rank)."""
+    return _stack_sharded(xs, ys, ts_all, ps, first, B, sensor_size, True, group)
+
+
+def events_to_stack_no_polarity_sharded(xs, ys, ts_all, ps, first, B, sensor_size=(180, 240), group=None):
+    """events_to_stack_no_polarity (reference encodings.py:202-238) of a split recording; see the polarity form."""
+    return _stack_sharded(xs, ys, ts_all, ps, first, B, sensor_size, False, group)

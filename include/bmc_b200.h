@@ -111,6 +111,15 @@ int bmc_encode_stack(float* xs, float* ys, const float* ts, float* ps, int64_t n
                      int H, int W, int polarity, float* out, void* workspace,
                      size_t workspace_bytes, unsigned flags, void* stream);
 
+/* The same encoders for ONE rank of a recording whose events are split into contiguous ranges across
+ * GPUs (SURVEY.md 8e "one giant grid"): this rank holds events [first, first + n_local) as xs, ys, ps; the
+ * bin boundaries are a property of the whole recording, so every rank passes the full ts_all[n_total] and
+ * evaluates them itself.  out is this rank's PARTIAL stack; the sum over ranks (one all-reduce of
+ * integer-valued floats, exact) equals bmc_encode_stack on the whole recording.  n_local may be 0. */
+int bmc_encode_stack_shard(float* xs, float* ys, float* ps, int64_t n_local, const float* ts_all,
+                           int64_t n_total, int64_t first, int bins, int H, int W, int polarity, float* out,
+                           void* workspace, size_t workspace_bytes, unsigned flags, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Model (reference: models/BMCNet.py, models/BMCNet_plain.py, models/submodules.py).
  * ---------------------------------------------------------------------------------------- */
