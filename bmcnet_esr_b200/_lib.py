@@ -7,7 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # BMC_B200_LIB selects another build (e.g. the bf16 variant made by `build.py --bf16`)
 LIB_PATH = os.environ.get('BMC_B200_LIB') or os.path.join(_HERE, 'libbmc_b200.so')
 
-ENC_FLIP_Y, ENC_MUTATE, ENC_NO_QUIRKS, ENC_TNORM, ENC_BILINEAR = 0x1, 0x2, 0x4, 0x8, 0x10
+ENC_FLIP_Y, ENC_MUTATE, ENC_NO_QUIRKS, ENC_TNORM, ENC_BILINEAR, ENC_SKIP_ZERO_ENDS = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20
 MODEL_BMCNET, MODEL_BMCNET_PLAIN = 0, 1
 
 _vp, _i, _i64, _f, _sz, _u = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint
@@ -34,6 +34,7 @@ SIGNATURES = {
     'bmc_format_events': (_i, [_vp, _vp, _vp, _vp, _i64, _vp, _vp]),
     'bmc_encode_image': (_i, [_vp, _vp, _vp, _i64, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_voxel': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
+    'bmc_encode_stack_flag_offset': (_sz, [_i64]),
     'bmc_encode_stack': (_i, [_vp, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_encode_stack_shard': (_i, [_vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _vp, _vp, _sz, _u, _vp]),
     'bmc_model_create': (_vp, [_i, _i, _i, _i, _i]),

@@ -402,13 +402,22 @@ __global__ void finalize_kernel(const int* __restrict__ cnt, const float* __rest
 // (float32, two roundings for ts[0] + delta_t*bi, any-equal binary search).  One thread per
 // (bin, side); ~3 log2(n) dependent loads each.
 // `shift` re-bases the boundaries for a rank that holds events [shift, shift + n_local) of the recording.
+// `zero_ends` (device int, always written): ts[0] == 0 && ts[n-1] == 0, the cheap necessary condition of the
+// reference's `ts.sum() == 0` early-out; with `skip_zero_ends` such a call gets empty bins (all-zero output, no
+// event touched) so that the host can decide the early-out AFTER the launch instead of synchronising before it.
 __global__ void bin_bounds_kernel(const float* __restrict__ ts, long n, int bins, long* beg,
-                                  long* end, long shift) {
+                                  long* end, long shift, int skip_zero_ends, int* zero_ends) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 2 * bins) return;
     const int bi = k >> 1;
     const bool right = k & 1;
     const float t0 = ts[0];
+    const bool ze = t0 == 0.f && ts[n - 1] == 0.f;
+    if (k == 0) *zero_ends = ze;
+    if (ze && skip_zero_ends) {
+        if (right) end[bi] = 0; else beg[bi] = 0;
+        return;
+    }
     const float dt = __fadd_rn(__fsub_rn(ts[n - 1], t0), 1e-6f);
     const float delta = __fdiv_rn(dt, (float)bins);
     const float tstart = __fadd_rn(t0, __fmul_rn(delta, (float)bi));
@@ -508,6 +517,8 @@ struct Ws {
 };
 
 size_t ws_bytes(long out_elems) { return (size_t)out_elems * 8 + 2 * 64 * sizeof(long) + 256; }
+// the stack encoders' `zero_ends` word sits right after the two boundary arrays, inside the 256 spare bytes
+size_t ws_flag_offset(long out_elems) { return (((size_t)out_elems * 8 + 15) & ~(size_t)15) + 2 * 64 * sizeof(long); }
 
 int carve(void* ws, size_t ws_bytes_given, long out_elems, Ws& w) {
     if (!ws || ws_bytes_given < ws_bytes(out_elems)) {
@@ -620,6 +631,7 @@ int check_common(const void* xs, const void* ys, const void* ps, long n, int H, 
 using namespace bmc;
 
 extern "C" BMC_EXPORT size_t bmc_encode_workspace_bytes(int64_t out_elems) { return ws_bytes(out_elems); }
+extern "C" BMC_EXPORT size_t bmc_encode_stack_flag_offset(int64_t out_elems) { return ws_flag_offset(out_elems); }
 
 extern "C" BMC_EXPORT int bmc_encode_channels(float* xs, float* ys, const float* ps, int64_t n, int H, int W,
                                    float* out, void* workspace, size_t workspace_bytes,
@@ -725,7 +737,9 @@ extern "C" BMC_EXPORT int bmc_encode_stack_shard(float* xs, float* ys, float* ps
     Ws w;
     rc = carve(workspace, workspace_bytes, elems, w);
     if (rc) return rc;
-    bin_bounds_kernel<<<1, 128, 0, as_stream(stream)>>>(ts_all, n_total, bins, w.beg, w.end, first);
+    bin_bounds_kernel<<<1, 128, 0, as_stream(stream)>>>(
+        ts_all, n_total, bins, w.beg, w.end, first, (flags & BMC_ENC_SKIP_ZERO_ENDS) ? 1 : 0,
+        reinterpret_cast<int*>(static_cast<char*>(workspace) + ws_flag_offset(elems)));
     BMC_CUDA(cudaGetLastError());
     StackOp op;
     op.xs = xs; op.ys = ys; op.ts = nullptr; op.ps = ps;

@@ -68,23 +68,16 @@ def events_to_voxel_sharded(xs, ys, ts, ps, num_bins, sensor_size=(180, 240), gr
 
 
 def _stack_sharded(xs, ys, ts_all, ps, first, B, sensor_size, polarity, group):
-    import torch
     from . import _lib
     from .dataloader import encodings as E
     n_local = E._chk(xs, ys, ps)
     E._chk(ts_all)
-    n_total = len(ts_all)
-    if first < 0 or first + n_local > n_total:
-        raise _lib.BmcError('events [%d, %d) outside the recording of %d' % (first, first + n_local, n_total))
-    eo = E._early_out(ts_all, B, sensor_size, xs.device)       # a property of the whole recording: same on all ranks
-    if eo is not None:
-        return eo
-    h, w = sensor_size
-    out = torch.empty(*((2, B, h, w) if polarity else (B, h, w)), dtype=torch.float32, device=xs.device)
-    E._run(lambda *a: _lib.lib().bmc_encode_stack_shard(E._p(xs), E._p(ys), E._p(ps), n_local, E._p(ts_all), n_total,
-                                                        int(first), B, h, w, int(polarity), *a, E._MUT,
-                                                        _lib.stream_ptr()), out)
-    return sum_grids(out, group)
+    if first < 0 or first + n_local > len(ts_all):
+        raise _lib.BmcError('events [%d, %d) outside the recording of %d' % (first, first + n_local, len(ts_all)))
+    out = E._stack_call(xs, ys, ps, ts_all, first, B, sensor_size, polarity)
+    if polarity and out.dim() == 3:        # the early-out: a property of the whole recording, same on every rank
+        return out
+    return sum_grids(out, group)           # (the no-polarity early-out is [B,H,W] zeros on every rank: summing is harmless)
 
 
 def events_to_stack_polarity_sharded(xs, ys, ts_all, ps, first, B, sensor_size=(180, 240), group=None):

@@ -55,6 +55,7 @@ const char* bmc_act_dtype(void);
 #define BMC_ENC_MUTATE 0x2u        /* reproduce the reference's in-place zeroing of out-of-range events */
 #define BMC_ENC_NO_QUIRKS 0x4u     /* drop the F9 leak of out-of-range events into pixel (0,0) */
 #define BMC_ENC_TNORM 0x8u         /* voxel: t = (ts-ts[0])/dt*(B-1) (encodings.py:127-129) instead of ts*(B-1) (:280) */
+#define BMC_ENC_SKIP_ZERO_ENDS 0x20u /* stacks: ts[0]==0 && ts[n-1]==0 -> all-zero output, no event touched (see below) */
 #define BMC_ENC_BILINEAR 0x10u     /* image: spatial bilinear splat into (H+1)x(W+1) (encodings.py:57-65) */
 
 /* Scratch bytes needed by any encoder call below for an output of `out_elems` floats. */
@@ -107,6 +108,12 @@ int bmc_encode_voxel(float* xs, float* ys, const float* ts, const float* ps, int
  * are evaluated on the device, so boundary events are double counted exactly as there.
  * The reference's early-out (ts.sum()==0 or n<=3 -> zeros[bins][H][W]) is the CALLER's job
  * (it changes the output shape); n <= 3 is rejected with BMC_ERR_ARG. */
+/* The early-out without a host round trip BEFORE the launch: every stack call stores the int
+ * (ts[0] == 0 && ts[n-1] == 0) at byte bmc_encode_stack_flag_offset(out_elems) of its workspace; with
+ * BMC_ENC_SKIP_ZERO_ENDS such a call leaves the events untouched and writes zeros, so the caller can launch first,
+ * read the word afterwards and only then -- in the rare case it is set -- scan ts and either return the
+ * reference's zeros or call again without the flag. */
+size_t bmc_encode_stack_flag_offset(int64_t out_elems);
 int bmc_encode_stack(float* xs, float* ys, const float* ts, float* ps, int64_t n, int bins,
                      int H, int W, int polarity, float* out, void* workspace,
                      size_t workspace_bytes, unsigned flags, void* stream);
