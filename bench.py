@@ -50,7 +50,8 @@ CONV_MAC_PER_PX = 147456          # 3x3 128->128
 # conv_slab2_tc, 2 jobs, 45x80: B=95: 193.4 + 143.0 MB (algorithmic 193.0 read + 193.0 written; part of the output is
 # still dirty in L2 when the kernel ends), B=57: 116.2 + 70.5 MB; encoders: bytes per event at 1e8 events
 # (12.04 / 16.04 for 12 / 16 algorithmic)
-NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): 336.4e6, ('plain', 57, 45, 80): 186.7e6}
+NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): 336.4e6, ('plain', 57, 45, 80): 186.7e6,
+                    ('full', 76, 45, 80): 569.8e6}       # 4 jobs, B=76: 309.2 MB read + 260.5 MB written
 NCU_ENC_BYTES_PER_EVENT, NCU_VOX_BYTES_PER_EVENT = 12.045, 16.035
 FLOP_PER_PX = {'plain': 9721856, 'full': 41574912}      # SURVEY 8d / BASELINE.md section 3
 
@@ -367,7 +368,7 @@ def main():
     peak = peaks.get('bf16_tflops', 1590.0)
     roofline = {'kernel': 'conv_slab2_tc (3x3 128->128 implicit GEMM, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
                 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                'traffic': NCU_CONV_TRAFFIC.get((model_kind, B, h, w)), 'traffic_unit': 'bytes per launch (ncu, profiles/r01_ncu_full_slab2_plain3x3.txt)',
+                'traffic': NCU_CONV_TRAFFIC.get((model_kind, B, h, w)), 'traffic_unit': 'bytes per launch (ncu, profiles/r01_ncu_full_slab2_%s3x3.txt)' % ('plain' if model_kind == 'plain' else 'bmcnet'),
                 'algorithmic_bytes': 2.0 * jobs * B * (((h + 2) * (w + 2) + 127) // 128 * 128) * 128 * 2,   # input read + output written
                 'us_per_launch': conv_ms * 1e3,
                 'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)'}
