@@ -12,7 +12,8 @@ each GPU: encode the step's two event windows per sequence into per-polarity cou
           (bmc_model_step), prediction written to HBM.
   e2e     through the reference-facing API (`model(x, h, o, init)` + `events_to_channels_windows`)
           with the step's events copied from pinned host memory and the prediction read back to
-          the host inside the timed region, every step.
+          the host inside the timed region, every step; timed 3 x K steps, the median run is reported
+          (all three are listed: the host side of a shared box is noisy).
   roofline  the dominant kernel (3x3 128->128 implicit-GEMM conv, tcgen05: conv_slab2_tc) timed live,
           back to back, at this workload's shape; algorithmic FLOPs = 2*147456 MAC per real LR pixel;
           `traffic` = DRAM bytes per launch of the committed ncu --set full capture (profiles/).
@@ -114,6 +115,7 @@ class ClockSampler:
                 'reasons': reasons, 'samples': len(sm)}
 
 
+E2E_RUNS = 3       # timed end-to-end regions of K steps each; the median is reported (see the e2e arm)
 CPU_BATCH = 8      # sequences per CPU step: a bounded sample of the GPU arm's batch (batching helps oneDNN: 8.8 -> 13.2 frames/s on 8 cores)
 
 
@@ -254,9 +256,8 @@ def main():
     launches = (model._engine.launches_per_step + 3) * Ksteps        # graph nodes + encode, pack, emit
 
     # ------------------------------------------------------------------ end-to-end arm
-    host_ev = torch.empty(total_steps + 1, 3, n_ev).pin_memory()       # +1: the pipeline uploads one step ahead
-    host_ev[:total_steps].copy_(stream)
-    host_ev[total_steps].copy_(stream[0])
+    host_ev = torch.empty(total_steps, 3, n_ev).pin_memory()           # step k reads row k % total_steps
+    host_ev.copy_(stream)
     host_pred = [torch.empty(B, 2, 4 * h, 4 * w).pin_memory() for _ in range(2)]
     dev_ev = [torch.empty(3, n_ev, device=dev) for _ in range(2)]
     n_state = 2 if model_kind == 'plain' else 4
@@ -275,7 +276,7 @@ def main():
     def upload(k):
         with torch.cuda.stream(copy_s):
             copy_s.wait_event(ev_used[k & 1])                                          # buffer free again
-            dev_ev[k & 1].copy_(host_ev[k], non_blocking=True)                         # H2D, pinned
+            dev_ev[k & 1].copy_(host_ev[k % total_steps], non_blocking=True)           # H2D, pinned
             ev_in[k & 1].record(copy_s)
 
     def step_e2e(k, st, init, last):
@@ -302,19 +303,25 @@ def main():
     upload(0)
     for k in range(Wsteps):
         st = step_e2e(k, st, k == 0, False)
-    copy_s.synchronize()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for k in range(Ksteps):
-        st = step_e2e(Wsteps + k, st, False, False)      # K uploads (of the next step's events) + K read-backs inside
-    main_s.wait_stream(copy_s)                                                       # the last read-back is inside the timed region
-    e1.record()
-    barrier()
-    ms_e2e = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e2e, op=dist.ReduceOp.MAX)
-    ms_e2e = ms_e2e.item()
+    # The end-to-end region depends on the host (PCIe, the Python thread): one run in ~6 on the shared boxes came out
+    # 1.5-2x slow with the device-resident number unchanged.  It is therefore timed E2E_RUNS times, each run EXACTLY
+    # K steps bracketed like the main region, and the MEDIAN is reported; all runs are listed in the JSON line.
+    e2e_runs = []
+    for run in range(E2E_RUNS):
+        copy_s.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(Ksteps):
+            st = step_e2e(Wsteps + run * Ksteps + k, st, False, False)    # K uploads (of the next step's events) + K read-backs inside
+        main_s.wait_stream(copy_s)                                                   # the last read-back is inside the timed region
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_runs.append(t.item())
+    ms_e2e = sorted(e2e_runs)[len(e2e_runs) // 2]
 
     if rank != 0:
         if world > 1:
@@ -418,7 +425,8 @@ def main():
                                   'activation arena %.0f MB' % (model._engine.weight_buf.numel() / 1e6,
                                                                 model._engine.workspace.numel() / 1e6)),
         'e2e': {'value': frames / (ms_e2e * 1e-3), 'unit': 'frames/s', 'ms_per_step': ms_e2e / Ksteps,
-                'h2d_bytes_per_step': 3 * n_ev * 4, 'd2h_bytes_per_step': B * 2 * 16 * h * w * 4},
+                'h2d_bytes_per_step': 3 * n_ev * 4, 'd2h_bytes_per_step': B * 2 * 16 * h * w * 4,
+                'runs_frames_per_s': [frames / (t * 1e-3) for t in e2e_runs], 'reported': 'median of %d runs of K steps' % E2E_RUNS},
         'gpu_launches': launches,
         'clocks': clocks,
         'roofline': roofline,
