@@ -399,41 +399,73 @@ __global__ void finalize_kernel(const int* __restrict__ cnt, const float* __rest
 }
 
 // Bin boundaries of the stack encoders, evaluated exactly like encodings.py:172-178 + :75-97
-// (float32, two roundings for ts[0] + delta_t*bi, any-equal binary search).  One thread per
-// (bin, side); ~3 log2(n) dependent loads each.
+// (float32, two roundings for ts[0] + delta_t*bi, any-equal binary search: every iteration tests ts[l], ts[r] and
+// ts[mid] for equality, in that order, before it halves the range).
+// One WARP per (bin, side).  The probe positions of the next five iterations form a binary tree that depends only
+// on (l, r), not on the data: lane k < 31 replays the path to heap node k with integer arithmetic, loads the three
+// stamps its node would test, and the warp then walks the tree through shuffles -- the reference's probe sequence
+// and comparisons exactly (also on unsorted input), in ~log2(n)/5 round trips to DRAM instead of log2(n).
 // `shift` re-bases the boundaries for a rank that holds events [shift, shift + n_local) of the recording.
 // `zero_ends` (device int, always written): ts[0] == 0 && ts[n-1] == 0, the cheap necessary condition of the
 // reference's `ts.sum() == 0` early-out; with `skip_zero_ends` such a call gets empty bins (all-zero output, no
 // event touched) so that the host can decide the early-out AFTER the launch instead of synchronising before it.
-__global__ void bin_bounds_kernel(const float* __restrict__ ts, long n, int bins, long* beg,
-                                  long* end, long shift, int skip_zero_ends, int* zero_ends) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kBoundsThreads = 128;
+__global__ void __launch_bounds__(kBoundsThreads) bin_bounds_kernel(
+    const float* __restrict__ ts, long n, int bins, long* beg, long* end, long shift, int skip_zero_ends,
+    int* zero_ends) {
+    const int k = (blockIdx.x * kBoundsThreads + threadIdx.x) >> 5;      // warp = (bin, side)
+    const int lane = threadIdx.x & 31;
     if (k >= 2 * bins) return;
     const int bi = k >> 1;
     const bool right = k & 1;
     const float t0 = ts[0];
     const bool ze = t0 == 0.f && ts[n - 1] == 0.f;
-    if (k == 0) *zero_ends = ze;
+    if (k == 0 && lane == 0) *zero_ends = ze;
     if (ze && skip_zero_ends) {
-        if (right) end[bi] = 0; else beg[bi] = 0;
+        if (lane == 0) { if (right) end[bi] = 0; else beg[bi] = 0; }
         return;
     }
     const float dt = __fadd_rn(__fsub_rn(ts[n - 1], t0), 1e-6f);
     const float delta = __fdiv_rn(dt, (float)bins);
     const float tstart = __fadd_rn(t0, __fmul_rn(delta, (float)bi));
     const float x = right ? __fadd_rn(tstart, delta) : tstart;
+
     long l = 0, r = n - 1, res = 0;
-    bool found = false;
-    while (l <= r) {
-        if (ts[l] == x) { res = l; found = true; break; }
-        if (ts[r] == x) { res = r; found = true; break; }
-        const long mid = l + (r - l) / 2;
-        const float mv = ts[mid];
-        if (mv == x) { res = mid; found = true; break; }
-        if (mv < x) l = mid + 1; else r = mid - 1;
+    bool found = false, done = false;
+    while (!done) {
+        // lane -> heap node (lane 31 idles): replay the path from the round's root; child 2k+1 = "ts[mid] < x"
+        long nl = l, nr = r;
+        bool valid = lane < 31 && nl <= nr;
+        const int idx = lane + 1;
+        const int depth = 31 - __clz(idx);
+        for (int d = depth - 1; d >= 0 && valid; --d) {
+            const long mid = nl + (nr - nl) / 2;
+            if ((idx >> d) & 1) nr = mid - 1; else nl = mid + 1;       // heap: left child 2k+1 has bit 0
+            valid = nl <= nr;
+        }
+        const long nmid = nl + (nr - nl) / 2;
+        float tl = 0.f, tr = 0.f, tm = 0.f;
+        if (valid) { tl = ts[nl]; tr = ts[nr]; tm = ts[nmid]; }
+        // walk five levels
+        int cur = 0;
+#pragma unroll 1
+        for (int level = 0; level < 5; ++level) {
+            const bool cv = __shfl_sync(0xffffffffu, (int)valid, cur);
+            const long cl = __shfl_sync(0xffffffffu, nl, cur), cr = __shfl_sync(0xffffffffu, nr, cur);
+            const long cm = __shfl_sync(0xffffffffu, nmid, cur);
+            const float vl = __shfl_sync(0xffffffffu, tl, cur), vr = __shfl_sync(0xffffffffu, tr, cur);
+            const float vm = __shfl_sync(0xffffffffu, tm, cur);
+            l = cl; r = cr;
+            if (!cv) { done = true; break; }                           // l > r: the search ended without a hit
+            if (vl == x) { res = cl; found = done = true; break; }
+            if (vr == x) { res = cr; found = done = true; break; }
+            if (vm == x) { res = cm; found = done = true; break; }
+            if (vm < x) { l = cm + 1; cur = 2 * cur + 1; } else { r = cm - 1; cur = 2 * cur + 2; }
+        }
+        if (!done && l > r) done = true;
     }
     if (!found) res = right ? r : l;
-    if (right) end[bi] = res + 1 - shift; else beg[bi] = res - shift;
+    if (lane == 0) { if (right) end[bi] = res + 1 - shift; else beg[bi] = res - shift; }
 }
 
 // One CTA per window (dataloader pattern: ~2048 events -> one [2,H,W] grid).  fp32 smem bins:
@@ -542,11 +574,18 @@ int launch_threads(const Op& op, long n, int nbins, const Ws& w, int vec_ok, siz
     auto kern = scatter_kernel<Op, MODE, THREADS>;
     if (smem > 48 * 1024)
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // Persistent grid: a multiple of the SM count, but never so many CTAs that flushing
-    // `nbins` bins per CTA outweighs the events each CTA streams.
+    // Persistent grid: a multiple of the SM count, but never so many CTAs that flushing their bins outweighs the
+    // events each CTA streams.  A CTA retires ~2 shared atomics per clock and flushes only its NON-ZERO bins, at
+    // the ~140 G/s of the L2 atomic units: g CTAs cost n/g / 3.8e9 + g * min(nbins, n/g) / 140e9 seconds.  While
+    // n/g < nbins the flush term is n / 140e9 whatever g is, so small streams on large grids (n < 37 nbins) take
+    // every SM; beyond that the minimum is at g = sqrt(36.8 n / nbins).
     long want = (n + (long)THREADS * 4 * 8 - 1) / ((long)THREADS * 4 * 8);
     if (MODE != kGlobal) {
         long by_flush = n / (4L * nbins) + 1;
+        const double ratio = 36.8 * (double)n / (double)nbins;
+        const long model = ratio < 36.8 * 37.0 ? (long)sm_count() * per_sm : (long)sqrt(ratio);
+        if (by_flush < model) by_flush = model;
+        want = (n + (long)THREADS * 4 - 1) / ((long)THREADS * 4);       // at least one 4-event group per thread
         if (want > by_flush) want = by_flush;
     }
     long grid = (long)sm_count() * per_sm;
@@ -737,7 +776,7 @@ extern "C" BMC_EXPORT int bmc_encode_stack_shard(float* xs, float* ys, float* ps
     Ws w;
     rc = carve(workspace, workspace_bytes, elems, w);
     if (rc) return rc;
-    bin_bounds_kernel<<<1, 128, 0, as_stream(stream)>>>(
+    bin_bounds_kernel<<<(2 * bins * 32 + kBoundsThreads - 1) / kBoundsThreads, kBoundsThreads, 0, as_stream(stream)>>>(
         ts_all, n_total, bins, w.beg, w.end, first, (flags & BMC_ENC_SKIP_ZERO_ENDS) ? 1 : 0,
         reinterpret_cast<int*>(static_cast<char*>(workspace) + ws_flag_offset(elems)));
     BMC_CUDA(cudaGetLastError());
