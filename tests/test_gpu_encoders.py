@@ -81,10 +81,10 @@ def test_against_reference_goldens(G, golden_dir, fname):
 
 
 @pytest.mark.parametrize('n,h,w,B', [(1, 5, 7, 3), (5, 5, 7, 2), (4097, 45, 80, 5), (200000, 45, 80, 5),
-                                     (150000, 180, 320, 3), (100000, 360, 640, 2), (70000, 31, 56, 9)])
+                                     (150000, 180, 320, 3), (450000, 180, 320, 5), (100000, 360, 640, 2), (70000, 31, 56, 9)])
 def test_against_oracle_random(G, n, h, w, B):
     """Seeded random streams incl. out-of-range, fractional and duplicate-timestamp events; every
-    histogram tier (smem int32 / packed 16-bit / global) is hit by one of the grid sizes."""
+    histogram tier (smem int32 / packed 16-bit / global / one time bin per CTA) is hit by one of the sizes."""
     ev = synth_events(n, h, w, seed=n % 97, oor=0.04, dup=True, frac=True)
     for name, fn in {**EXACT, **FLOAT}.items():
         ca, ga = [x.copy() for x in ev], _gpu(ev)
@@ -217,3 +217,27 @@ def test_full_size_voxel_and_stack_properties(G):
     lo, hi = int(edges[1]) + 8, int(edges[2]) - 8                     # strictly inside bin 2
     mid = G.events_to_image_torch(xs[lo:hi].contiguous(), ys[lo:hi].contiguous(), ps[lo:hi].contiguous(), sensor_size=(h, w))
     assert float((sn[2] - mid).abs().max()) <= 16.0                   # up to 8 events on either side of the slice
+
+
+def test_stack_one_bin_per_cta_kernel_unaligned_and_sharded(G):
+    """stack_bins_kernel (grids whose planes fit shared memory only one time bin at a time): a 4-byte-aligned view
+    (scalar path), and two event ranges through the shard entry, against the oracle on the whole stream."""
+    from bmcnet_esr_b200 import sharding as S
+    n, h, w, B = 500_001, 180, 320, 5
+    ev = synth_events(n, h, w, seed=21, oor=0.03, dup=True, frac=True)
+    for pol, name in ((True, 'stack_polarity'), (False, 'stack_no_polarity')):
+        ref = EXACT[name](E, [x[1:].copy() for x in ev], h, w, B)
+        odd = [t[1:] for t in _gpu(ev)]                            # contiguous views with data_ptr % 16 == 4
+        assert odd[0].data_ptr() % 16 == 4
+        got = EXACT[name](G, odd, h, w, B).cpu().numpy()
+        assert np.array_equal(got, ref), name
+        # two ranks' worth of events, summed by hand
+        full = [x[1:].copy() for x in ev]
+        ts_all = torch.from_numpy(full[2]).cuda()
+        acc = None
+        for lo, hi in ((0, 233_332), (233_332, len(full[0]))):
+            cut = [torch.from_numpy(full[i][lo:hi].copy()).cuda() for i in (0, 1, 3)]
+            fn = S.events_to_stack_polarity_sharded if pol else S.events_to_stack_no_polarity_sharded
+            part = fn(cut[0], cut[1], ts_all, cut[2], lo, B, sensor_size=(h, w))
+            acc = part if acc is None else acc + part
+        assert np.array_equal(acc.cpu().numpy(), ref), name + ' sharded'
