@@ -225,11 +225,69 @@ def make_redistribute_golden():
     np.savez_compressed(os.path.join(GOLD, 'redistribute.npz'), **out)
 
 
+def _stats(t, k=24):
+    """Compact fingerprint of a tensor: sum, abs-sum (float64) and its first k values."""
+    f = t.detach().double().flatten()
+    return np.concatenate([[f.sum().item(), f.abs().sum().item()], f[:k].numpy(), np.zeros(max(0, k - f.numel()))])
+
+
+def make_train_goldens():
+    """Two training iterations of the REFERENCE (its nn.Modules, nn.MSELoss, torch.optim.Adam(amsgrad)) on seeded
+    data, the way train.py:202-237 runs them; fingerprints of every unique parameter's gradient (iteration 1) and
+    value (after iteration 2) pin oracle/train_step.py."""
+    sys.path.insert(0, REF)
+    from models.BMCNet import BMCNet
+    from models.BMCNet_plain import BMCNet_plain
+    from oracle import bmcnet_fp32 as O
+
+    for plain, tag, gt_hw in ((True, 'plain', (40, 64)), (False, 'bmcnet', (38, 62))):     # (38,62): bicubic resize path
+        b, h, w, T = 1, 10, 16, 3
+        sd = O.surrogate_state_dict(plain=plain, seed=2024)
+        m = (BMCNet_plain if plain else BMCNet)(4, 128, 5)
+        m.load_state_dict(sd, strict=True)
+        m.train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, weight_decay=1e-5, amsgrad=True)    # train_nfs.yml:28-34
+        mse = torch.nn.MSELoss()
+        xs = [synth_counts(b, h, w, 700 + s) for s in range(T)]
+        g = torch.Generator().manual_seed(77)
+        gts = [torch.poisson(torch.full((b, 2) + gt_hw, 0.3), generator=g) for _ in range(T)]
+        names = {id(p): O._alias_root(n) for n, p in m.named_parameters()}
+        out = {'x': np.stack([x.numpy() for x in xs]), 'gt': np.stack([t.numpy() for t in gts]), 'losses': []}
+        for it in range(2):
+            opt.zero_grad()
+            loss, init, st = 0, True, None
+            for x, gt in zip(xs, gts):                                              # train.py:206-234
+                if init:
+                    z = torch.zeros_like(x[:, 0:1, 0])
+                    st = [z.repeat(1, 128, 1, 1)] * (1 if plain else 3) + [z.repeat(1, 32, 1, 1)]
+                st = list(m(x, *st, init))
+                init = False
+                pred = st[-1]
+                if pred.shape[-2:] != gt.shape[-2:]:
+                    pred = torch.nn.functional.interpolate(pred, size=gt.shape[-2:], mode='bicubic', align_corners=False)
+                loss = loss + mse(pred, gt)
+            loss.backward()
+            if it == 0:
+                for p in m.parameters():
+                    out['grad.' + names[id(p)]] = _stats(p.grad)
+            opt.step()
+            out['losses'].append(loss.item())
+        for p in m.parameters():
+            out['param.' + names[id(p)]] = _stats(p)
+        out['losses'] = np.array(out['losses'])
+        np.savez_compressed(os.path.join(GOLD, 'train_step_%s.npz' % tag), torch=torch.__version__, **out)
+        print('train golden', tag, out['losses'], len([k for k in out if k.startswith('grad.')]), 'unique parameters')
+
+
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
+    if 'train' in sys.argv[1:]:
+        make_train_goldens()
+        sys.exit(0)
     make_encoder_goldens()
     make_model_goldens()
     total = sum(os.path.getsize(os.path.join(GOLD, f)) for f in os.listdir(GOLD))
     print('golden bytes', total)
     make_format_golden()
     make_redistribute_golden()
+    make_train_goldens()

@@ -165,3 +165,64 @@ def test_sequence_tuples_are_views_of_consecutive_windows():
     assert torch.equal(item[0].transpose(1, 2)[0, :, 1], cnt[2])            # input_stack = inp_cnt.transpose(1, 2), infer_BMCNet.py:50
     with pytest.raises(IndexError):
         sequence_item(cnt, 3, sequence_length=5)
+
+
+# ---- training iteration: oracle/train_step.py against the reference's own modules + Adam ----
+import pytest as _pytest
+
+
+@_pytest.mark.parametrize('tag', ['plain', 'bmcnet'])
+def test_train_iteration_matches_reference(golden_dir, tag):
+    """Two iterations of train.py:202-237 (sequence loss from zero state, one backward, Adam(amsgrad) with weight
+    decay): losses, every unique parameter's gradient fingerprint after iteration 1 and value after iteration 2."""
+    import numpy as np
+    import torch
+    from oracle import bmcnet_fp32 as O
+    from oracle import train_step as T
+    g = np.load(os.path.join(golden_dir, 'train_step_%s.npz' % tag))
+    plain = tag == 'plain'
+    sd = O.surrogate_state_dict(plain=plain, seed=2024)
+    xs = [torch.from_numpy(a) for a in g['x']]
+    gts = [torch.from_numpy(a) for a in g['gt']]
+
+    def stats(t, k=24):
+        f = t.detach().double().flatten()
+        return np.concatenate([[f.sum().item(), f.abs().sum().item()], f[:k].numpy(), np.zeros(max(0, k - f.numel()))])
+
+    state, losses = None, []
+    for it in range(2):
+        loss, grads, params, state = T.train_iteration(sd, xs, gts, plain, opt_state=state)
+        losses.append(loss.item())
+        if it == 0:
+            keys = [k[5:] for k in g.files if k.startswith('grad.')]
+            assert sorted(keys) == sorted(grads), 'unique-parameter set differs from the reference'
+            for k in keys:
+                want, got = g['grad.' + k], stats(grads[k])
+                scale = max(1e-12, want[1] / max(1, grads[k].numel()))          # mean |grad|
+                assert abs(got[0] - want[0]) <= 2e-3 * want[1] + 1e-9, (k, got[0], want[0])
+                assert abs(got[1] - want[1]) <= 1e-3 * want[1] + 1e-9, (k, got[1], want[1])
+                assert np.abs(got[2:] - want[2:]).max() <= 2e-2 * scale + 1e-3 * np.abs(want[2:]).max(), k
+        sd = {k: params[O._alias_root(k)] for k in sd}              # next iteration sees the updated weights
+    assert np.allclose(losses, g['losses'], rtol=1e-5), (losses, g['losses'])
+    for k in [k[6:] for k in g.files if k.startswith('param.')]:
+        want, got = g['param.' + k], stats(params[k])
+        assert np.abs(got[2:] - want[2:]).max() <= 2e-6 + 1e-5 * np.abs(want[2:]).max(), k     # lr = 1e-4 steps
+        assert abs(got[1] - want[1]) <= 1e-5 * want[1] + 1e-9, k
+
+
+def test_adam_amsgrad_restatement_matches_torch():
+    import torch
+    from oracle import train_step as T
+    torch.manual_seed(0)
+    p0 = {'a': torch.randn(7, 5), 'b': torch.randn(11)}
+    ref = {k: v.clone().requires_grad_(True) for k, v in p0.items()}
+    opt = torch.optim.Adam(ref.values(), lr=1e-3, weight_decay=1e-2, amsgrad=True)
+    mine, state = {k: v.clone() for k, v in p0.items()}, {}
+    for step in range(5):
+        grads = {k: torch.randn_like(v) * (0.1 if step == 3 else 1.0) for k, v in p0.items()}      # a small step exercises vmax
+        for k in ref:
+            ref[k].grad = grads[k].clone()
+        opt.step()
+        T.adam_amsgrad_step(mine, grads, state, lr=1e-3, weight_decay=1e-2)
+    for k in ref:
+        assert torch.allclose(mine[k], ref[k].detach(), rtol=1e-6, atol=1e-7), k
