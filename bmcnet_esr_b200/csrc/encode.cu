@@ -439,14 +439,18 @@ __global__ void __launch_bounds__(kBinThreads) stack_bins_kernel(StackOp op, lon
             return;
         }
         // out of range (rare): the first bin that holds the event zeroes it in place, later bins see (0,0)
-        bool first = true;
-        for (int e = 0; e < b; ++e) first = first && !(s_beg[e] <= i && i < s_end[e]);
+        bool first = true, multi = false;
+        for (int e = 0; e < op.bins; ++e)
+            if (e != b && s_beg[e] <= i && i < s_end[e]) { multi = true; first = first && e > b; }
         if (POL && op.quirks() && (!first || p < 0.f)) {
             const float w = p * p;
             const long gi = gbase + (p < 0.f ? gneg : 0);
             if (w == 1.f) atomicAdd(&g_cnt[gi], 1); else if (w != 0.f) atomicAdd(&g_ext[gi], w);
         }
-        if (op.mutate()) { op.xs[i] = 0.f; op.ys[i] = 0.f; if (!POL) op.ps[i] = 0.f; }
+        // An event of ONE bin is used by this thread alone and is zeroed here.  An event of several bins is also
+        // read by other CTAs: nobody touches it while this kernel runs (stack_bins_mutate_kernel does afterwards),
+        // so every CTA sees the original coordinates whatever the order they run in.
+        if (op.mutate() && !multi) { op.xs[i] = 0.f; op.ys[i] = 0.f; if (!POL) op.ps[i] = 0.f; }
     };
 
     if (hi > lo) {
@@ -480,6 +484,22 @@ __global__ void __launch_bounds__(kBinThreads) stack_bins_kernel(StackOp op, lon
             if (v >> 16) atomicAdd(&g_cnt[gbase + (L1 >= plane ? gneg + L1 - plane : L1)], (int)(v >> 16));
         } else if (v) {
             atomicAdd(&g_cnt[gbase + k], (int)v);
+        }
+    }
+}
+
+// The in-place zeroing (encodings.py:37-39) of out-of-range events that lie in MORE than one time bin, left alone by
+// stack_bins_kernel: CTA b walks the intersections of bin b with every later bin.
+template <bool POL>
+__global__ void stack_bins_mutate_kernel(StackOp op, long n) {
+    const int b = blockIdx.x;
+    for (int e = b + 1; e < op.bins; ++e) {
+        const long lo = max(0L, max(op.beg[b], op.beg[e])), hi = min(n, min(op.end[b], op.end[e]));
+        for (long i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            if (decode_xy(op.xs[i], op.ys[i], op.H, op.W, false).oor) {
+                op.xs[i] = 0.f; op.ys[i] = 0.f;
+                if (!POL) op.ps[i] = 0.f;
+            }
         }
     }
 }
@@ -893,6 +913,11 @@ extern "C" BMC_EXPORT int bmc_encode_stack_shard(float* xs, float* ys, float* ps
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem));
         kern<<<sm_count(), kBinThreads, bin_smem, st>>>(op, n_local, w.cnt, w.ext, vec_ok);
         BMC_CUDA(cudaGetLastError());
+        if ((flags & BMC_ENC_MUTATE) && bins > 1) {
+            if (polarity) stack_bins_mutate_kernel<true><<<bins - 1, 256, 0, st>>>(op, n_local);
+            else stack_bins_mutate_kernel<false><<<bins - 1, 256, 0, st>>>(op, n_local);
+            BMC_CUDA(cudaGetLastError());
+        }
         const int thr = 256;
         finalize_kernel<<<(unsigned)((elems + thr - 1) / thr), thr, 0, st>>>(w.cnt, w.ext, out, elems);
         BMC_CUDA(cudaGetLastError());
