@@ -101,18 +101,26 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(',')])
 
+    def mark(self):
+        """The timed region starts now: only samples that arrive from here on are reported.  (nvidia-smi needs
+        100-300 ms to deliver its first sample, so the process is started before the warm-up steps.)"""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         time.sleep(0.15)
         self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        rows, window = self.rows[getattr(self, 'first', 0):], 'timed region'
+        if not any(r and r[0].isdigit() for r in rows):       # region shorter than the sampling period
+            rows, window = self.rows, 'warm-up + timed region (the timed region was shorter than one sampling period)'
+        sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == 'Active'})
+        reasons = sorted({n for r in rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v == 'Active'})
         busy = [v for v in sm if mx and v > 0.5 * mx[0]] or sm
         return {'sm_mhz': busy[len(busy) // 2] if busy else None, 'sm_max_mhz': mx[0] if mx else None,
-                'reasons': reasons, 'samples': len(sm)}
+                'reasons': reasons, 'samples': len(sm), 'window': window}
 
 
 E2E_RUNS = 3       # timed end-to-end regions of K steps each; the median is reported (see the e2e arm)
@@ -238,10 +246,12 @@ def main():
         x = cnt.view(B, 2, 2, h, w).transpose(1, 2)              # [B,2,T,H,W] view, as infer_BMCNet.py:50
         return model.step(x, reset=reset)
 
+    sampler = ClockSampler(local_rank) if rank == 0 else None
     for k in range(Wsteps):
         step_resident(k, k == 0)
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.mark()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for k in range(Ksteps):
