@@ -895,17 +895,18 @@ int bie_front_slots(int total_tiles, int tiles_per_img) {
 }
 
 int launch_bie_front(const BieFrontParams& p, cudaStream_t st) {
-    static bool configured = false;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (!configured) {
         BMC_CUDA(cudaFuncSetAttribute(bie_front_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kFrontSmem));
-        configured = true;
+        configured = 1;
     }
     const int grid = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
     static long long* prof = nullptr;
     static int prof_init = 0, dumped = 0;
     if (!prof_init) {
         prof_init = 1;
-        if (getenv("BMC_FRONT_PROF")) { cudaMalloc(&prof, 148 * 16 * sizeof(long long)); cudaMemset(prof, 0, 148 * 16 * sizeof(long long)); }
+        if (measure_env("BMC_FRONT_PROF", 0)) { cudaMalloc(&prof, 148 * 16 * sizeof(long long)); cudaMemset(prof, 0, 148 * 16 * sizeof(long long)); }
     }
     BieFrontParams q = p;
     q.prof = prof;
@@ -925,10 +926,11 @@ int launch_bie_front(const BieFrontParams& p, cudaStream_t st) {
 }
 
 int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream_t st) {
-    static bool configured = false;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (!configured) {
         BMC_CUDA(cudaFuncSetAttribute(att_fold_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldTcSmem));
-        configured = true;
+        configured = 1;
     }
     BMC_CUDA(launch_pdl(att_fold_tc, dim3(p.n_inst * p.B * 2 * (128 / kFoldTcRows)), dim3(kFoldTcThreads), (size_t)kFoldTcSmem, st, p, map_w));
     BMC_CUDA(cudaGetLastError());
@@ -937,13 +939,14 @@ int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream
 
 int launch_att_fold(const FoldParams& p, cudaStream_t st) {
     const int smem = (128 * kFoldLd + kFoldRows * 128) * (int)sizeof(float);
-    static bool configured = false;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (!configured) {
         BMC_CUDA(cudaFuncSetAttribute(att_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured = 1;
     }
     static int dbg = -1, calls = 0;
-    if (dbg < 0) dbg = getenv("BMC_FOLD_PROF") ? 1 : 0;
+    if (dbg < 0) dbg = measure_env("BMC_FOLD_PROF", 0) ? 1 : 0;
     FoldParams q = p;
     q.dbg = dbg && ++calls == 8;
     att_fold<<<p.n_inst * p.B * 2 * (128 / kFoldRows), kFoldThreads, smem, st>>>(q);

@@ -50,8 +50,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
-// Number of SMs of the current device (148 on B200); cached.
+// Number of SMs of the current device (148 on B200); cached per device.
 int sm_count();
+
+// Measurement switches exist only in a -DBMC_MEASURE build (`build.py --measure`):
+// there `measure_env` reads an integer from the environment; in the product library it is the constant default,
+// so no environment variable can change what a kernel computes.
+#ifdef BMC_MEASURE
+int measure_env(const char* name, int dflt);
+#else
+inline int measure_env(const char*, int dflt) { return dflt; }
+#endif
+
+// Per-device "already done" state for one call site (shared-memory attributes are per device and function; two
+// devices driven from one process each need their own cudaFuncSetAttribute).
+struct PerDevice {
+    int v[64] = {};
+    int& cur();                     // slot of the calling thread's current device
+};
 
 // Launch with programmatic dependent launch -- OFF by default, BMC_PDL=1 enables it (measured on B200: the
 // persistent kernels fill shared memory, a successor cannot become resident before a predecessor CTA exits, and

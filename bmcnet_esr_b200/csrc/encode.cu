@@ -720,7 +720,7 @@ int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaSt
     // flushes its bins once per SM instead of once per 512-thread CTA: with 4 CTAs per SM the flush of a 7200-bin
     // grid was 4.3 M global atomics, 17 % of a 1e8-event launch.  Small streams keep the finer grid.
     static int fat = -1;
-    if (fat < 0) { const char* e = getenv("BMC_ENC_FAT"); fat = e ? atoi(e) : 1; }
+    if (fat < 0) fat = measure_env("BMC_ENC_FAT", 1);
     if (per_sm < 2 || (fat && MODE != kGlobal && n >= (long)sm_count() * 1024 * 64))
         return launch_threads<Op, MODE, 1024>(op, n, nbins, w, vec_ok, smem, 1, st);
     return launch_threads<Op, MODE, kThreads>(op, n, nbins, w, vec_ok, smem, per_sm > 4 ? 4 : per_sm, st);
@@ -901,7 +901,7 @@ extern "C" BMC_EXPORT int bmc_encode_stack_shard(float* xs, float* ys, float* ps
     op.H = H; op.W = W; op.bins = bins; op.flags = flags & ~BMC_ENC_FLIP_Y;
     op.beg = w.beg; op.end = w.end; op.polarity = polarity;
     static int by_bin = -1;
-    if (by_bin < 0) { const char* e = getenv("BMC_ENC_STACK_BINS"); by_bin = e ? atoi(e) : 1; }
+    if (by_bin < 0) by_bin = measure_env("BMC_ENC_STACK_BINS", 1);
     const size_t bin_smem = (size_t)H * W * 4;
     if (by_bin && elems > kMaxBinsSmem32 && bin_smem + 2048 <= (size_t)kSmemBudget && bins <= sm_count() &&
         n_local >= (long)bins * 65536) {

@@ -277,7 +277,7 @@ int pair_smem(int slab_boxes) { return kSlabStages * slab_boxes * kBoxBytes + kW
 // TMA maps (a_map64 / w_map64), on an even grid.
 bool pair_supported(const GemmParams& p) {
     static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("BMC_CONV_PAIR"); enabled = e ? atoi(e) : 0; }   // off by default: measured slower than the single-CTA slab kernel
+    if (enabled < 0) enabled = measure_env("BMC_CONV_PAIR", 0);   // off by default: measured slower than the single-CTA slab kernel
     if (!enabled || p.n != kN) return false;
     for (int j = 0; j < p.n_jobs; ++j) {
         if (p.jobs[j].w_img_stride != 0 || p.jobs[j].w_map64 <= 0) return false;
@@ -298,7 +298,8 @@ int launch_conv_pair(GemmParams p, cudaStream_t st) {
     p.pairs_per_job = (int)((p.g.rows() + 2 * kBM - 1) / (2 * kBM));
     if (p.abox_rows <= 0) p.abox_rows = kBoxRows;
     const int smem = pair_smem(p.slab_boxes);
-    static int configured = 0;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (configured < smem) {
         BMC_CUDA(cudaFuncSetAttribute(conv_pair_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
@@ -310,7 +311,7 @@ int launch_conv_pair(GemmParams p, cudaStream_t st) {
     static int prof_init = 0, dumped = 0;
     if (!prof_init) {
         prof_init = 1;
-        if (getenv("BMC_PAIR_PROF")) { cudaMalloc(&prof, 74 * 16 * sizeof(long long)); cudaMemset(prof, 0, 74 * 16 * sizeof(long long)); }
+        if (measure_env("BMC_PAIR_PROF", 0)) { cudaMalloc(&prof, 74 * 16 * sizeof(long long)); cudaMemset(prof, 0, 74 * 16 * sizeof(long long)); }
     }
     p.prof = prof;
     conv_pair_tc<<<2 * clusters, kThreadsPair, smem, st>>>(p);

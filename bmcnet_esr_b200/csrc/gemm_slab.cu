@@ -361,7 +361,8 @@ template <int N>
 int launch_slab_n(const GemmParams& p, cudaStream_t st) {
     auto kern = conv_slab_tc<N>;
     const int smem = kSlabStages * p.slab_boxes * kBoxBytes + kWStages * kWGroup * N * kChunkK * 2 + 8 * 2048 + 1024;
-    static int configured = 0;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (configured < smem) {
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         configured = smem;
@@ -421,13 +422,13 @@ int launch_conv_slab(GemmParams p, cudaStream_t st) {
     // 0 (default, verified on B200): the hardware swizzles on absolute shared-memory address bits,
     // so a row-shifted start needs no base offset; 1 sets the descriptor's base-offset field
     // (measured WRONG results -- kept only as an experiment switch).
-    if (bo < 0) { const char* e = getenv("BMC_SLAB_BO"); bo = e ? atoi(e) : 0; }
+    if (bo < 0) bo = measure_env("BMC_SLAB_BO", 0);
     p.bo_mode = bo;
     static long long* prof = nullptr;
     static int prof_init = 0;
     if (!prof_init) {
         prof_init = 1;
-        if (getenv("BMC_SLAB_PROF")) { cudaMalloc(&prof, 148 * 16 * sizeof(long long)); cudaMemset(prof, 0, 148 * 16 * sizeof(long long)); }
+        if (measure_env("BMC_SLAB_PROF", 0)) { cudaMalloc(&prof, 148 * 16 * sizeof(long long)); cudaMemset(prof, 0, 148 * 16 * sizeof(long long)); }
     }
     p.prof = prof;
     if (prof) {

@@ -490,7 +490,7 @@ static int slab2_smem(const Geom& g, int n_taps) {
 
 bool slab2_supported(const GemmParams& p) {
     static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("BMC_CONV_SLAB2"); enabled = e ? atoi(e) : 1; }
+    if (enabled < 0) enabled = measure_env("BMC_CONV_SLAB2", 1);
     if (!enabled || !p.has32 || p.n != kN || (p.n_taps != 9 && p.n_taps != 1) || (p.tap1_mask & 1)) return false;
     int steps = 0;
     for (int s = 0; s < p.n_seg; ++s) steps += 2 * p.chunks[s];
@@ -534,35 +534,42 @@ int launch_conv_slab2(GemmParams p, cudaStream_t st) {
         }
     }
     const int smem = slab2_smem(p.g, p.n_taps);
-    static int configured = 0;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (configured < smem) {
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#ifdef BMC_MEASURE
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        BMC_CUDA(cudaFuncSetAttribute(conv_slab2_tc<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+#endif
         configured = smem;
     }
     int grid = p.n_full < sm_count() ? p.n_full : sm_count();
     {   // measurement switch: fewer CTAs -> is a tile's time set by the SM or by the shared L2 fabric?
         static int cap = -1;
-        if (cap < 0) { const char* e = getenv("BMC_SLABT_GRID"); cap = e ? atoi(e) : 0; }
+        if (cap < 0) cap = measure_env("BMC_SLABT_GRID", 0);
         if (cap > 0 && grid > cap) grid = cap;
     }
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("BMC_SLAB2_DBG"); dbg = e ? atoi(e) : 0; }
     bool tma_out = true;
     for (int j = 0; j < p.n_jobs; ++j) tma_out = tma_out && p.jobs[j].out_map32 >= 0;
-    if (dbg == 1) BMC_CUDA(launch_pdl(conv_slab2_tc<1>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
-    else if (dbg == 2) BMC_CUDA(launch_pdl(conv_slab2_tc<2>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
-    else if (dbg == 3) BMC_CUDA(launch_pdl(conv_slab2_tc<3>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
-    else if (dbg == 4) BMC_CUDA(launch_pdl(conv_slab2_tc<4>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
-    else if (dbg == 8) BMC_CUDA(launch_pdl(conv_slab2_tc<8>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
-    else if (dbg == 32 && tma_out) BMC_CUDA(launch_pdl(conv_slab2_tc<32>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));
-    else if (dbg == 0 && tma_out) BMC_CUDA(launch_pdl(conv_slab2_tc<32>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));     // product path: TMA-store epilogue
-    else BMC_CUDA(launch_pdl(conv_slab2_tc<0>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));                               // outputs without a tensor map / BMC_SLAB2_DBG=64
+#ifdef BMC_MEASURE
+    // measurement builds of the kernel (stale-operand MMAs, dropped stores, ...): they do NOT compute the
+    // convolution and exist only in `build.py --measure` libraries
+    static int dbg = -1;
+    if (dbg < 0) dbg = measure_env("BMC_SLAB2_DBG", 0);
+    if (dbg == 1) { BMC_CUDA(launch_pdl(conv_slab2_tc<1>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p)); return BMC_OK; }
+    if (dbg == 2) { BMC_CUDA(launch_pdl(conv_slab2_tc<2>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p)); return BMC_OK; }
+    if (dbg == 3) { BMC_CUDA(launch_pdl(conv_slab2_tc<3>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p)); return BMC_OK; }
+    if (dbg == 4) { BMC_CUDA(launch_pdl(conv_slab2_tc<4>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p)); return BMC_OK; }
+    if (dbg == 8) { BMC_CUDA(launch_pdl(conv_slab2_tc<8>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p)); return BMC_OK; }
+    if (dbg == 64) tma_out = false;
+#endif
+    if (tma_out) BMC_CUDA(launch_pdl(conv_slab2_tc<32>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));     // product path: TMA-store epilogue
+    else BMC_CUDA(launch_pdl(conv_slab2_tc<0>, dim3(grid), dim3(kThreads2), (size_t)smem, st, p));              // outputs without a tensor map
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

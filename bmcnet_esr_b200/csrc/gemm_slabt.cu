@@ -370,7 +370,7 @@ int slabt_smem(int slab_boxes) { return kSlabStages * slab_boxes * kBoxBytes + k
 
 bool slabt_supported(const GemmParams& p) {
     static int enabled = -1;
-    if (enabled < 0) { const char* e = getenv("BMC_CONV_SLABT"); enabled = e ? atoi(e) : 1; }
+    if (enabled < 0) enabled = measure_env("BMC_CONV_SLABT", 1);
     if (!enabled || p.n != kN || (p.n_taps != 9 && p.n_taps != 1) || (p.tap1_mask & 1)) return false;
     for (int j = 0; j < p.n_jobs; ++j) {
         const GemmJobDev& d = p.jobs[j];
@@ -394,7 +394,8 @@ int launch_conv_slabt(GemmParams p, cudaStream_t st) {
     p.n_full = p.n_jobs * (int)((p.g.rows() + kBM - 1) / kBM);
     p.n_half = 0;
     const int smem = slabt_smem(p.slab_boxes);
-    static int configured = 0;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (configured < smem) {
         BMC_CUDA(cudaFuncSetAttribute(conv_slabt_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         BMC_CUDA(cudaFuncSetAttribute(conv_slabt_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -404,13 +405,13 @@ int launch_conv_slabt(GemmParams p, cudaStream_t st) {
     for (int j = 0; j < p.n_jobs; ++j) tma_out = tma_out && p.jobs[j].out_map32 >= 0;
     {
         static int direct = -1;        // BMC_SLABT_DIRECT=1: force the register epilogue (measurement)
-        if (direct < 0) { const char* e = getenv("BMC_SLABT_DIRECT"); direct = e ? atoi(e) : 0; }
+        if (direct < 0) direct = measure_env("BMC_SLABT_DIRECT", 0);
         if (direct) tma_out = false;
     }
     int grid = p.n_full < sm_count() ? p.n_full : sm_count();
     {   // measurement switch: fewer CTAs -> is a tile's time set by the SM or by the shared L2 fabric?
         static int cap = -1;
-        if (cap < 0) { const char* e = getenv("BMC_SLABT_GRID"); cap = e ? atoi(e) : 0; }
+        if (cap < 0) cap = measure_env("BMC_SLABT_GRID", 0);
         if (cap > 0 && grid > cap) grid = cap;
     }
     if (tma_out) BMC_CUDA(launch_pdl(conv_slabt_tc<true>, dim3(grid), dim3(kThreadsT), (size_t)smem, st, p));

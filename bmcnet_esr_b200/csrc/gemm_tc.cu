@@ -246,10 +246,11 @@ template <int N, int STAGES>
 int launch_tc(const GemmParams& p, cudaStream_t st) {
     auto kern = conv_gemm_tc<N, STAGES>;
     const int smem = STAGES * TcCfg<N>::kStageBytes + 1024;
-    static bool configured = false;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (!configured) {
         BMC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured = 1;
     }
     dim3 grid((unsigned)(p.g.B * p.tiles_per_img), (unsigned)p.n_jobs);
     kern<<<grid, kThreadsTc, smem, st>>>(p);
@@ -262,14 +263,22 @@ int launch_tc(const GemmParams& p, cudaStream_t st) {
 int launch_conv_gemm_simt(const GemmParams& p, cudaStream_t st);
 int launch_att_simt(const AttParams& p, cudaStream_t st);
 
+#ifdef BMC_MEASURE
+// conv_pair_tc (gemm_pair.cu, cta_group::2): measured slower than the single-CTA slab kernels;
+// compiled into `build.py --measure` libraries only
 static bool use_pair_ok(const GemmParams& p) { return p.jobs[0].a_map64[0] >= 0 && slab_supported(p) && pair_supported(p); }
+#else
+static bool use_pair_ok(const GemmParams&) { return false; }
+#endif
 
 int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
     if (p.tap1_mask && (impl != 0 || p.jobs[0].a_map64[0] < 0 || !slab_supported(p))) {
         set_error("conv_gemm: centre-tap segments exist only in the slab kernel");
         return BMC_ERR_UNSUPPORTED;
     }
+#ifdef BMC_MEASURE
     if (impl == 0 && use_pair_ok(p)) return launch_conv_pair(p, st);
+#endif
     // conv_slab2_tc wins on launches made of 3x3 segments only; launches with centre-tap segments (one short
     // phase per 32 channels, each with its own slab) are faster on conv_slabt_tc (measured)
     if (impl == 0 && !p.tap1_mask && slab2_supported(p)) return launch_conv_slab2(p, st);
@@ -277,12 +286,11 @@ int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
     if (p.tap1_mask) return launch_conv_slab(p, st);
     if (impl == 1) return launch_conv_gemm_simt(p, st);
     static int use_slab = -1;
-    if (use_slab < 0) { const char* e = getenv("BMC_CONV_SLAB"); use_slab = e ? atoi(e) : 1; }
+    if (use_slab < 0) use_slab = measure_env("BMC_CONV_SLAB", 1);
     if (impl == 0 && use_slab && p.jobs[0].a_map64[0] >= 0 && slab_supported(p)) return launch_conv_slab(p, st);
     static int stages = 0;
     if (stages == 0) {
-        const char* e = getenv("BMC_TC_STAGES");
-        stages = e ? atoi(e) : 3;
+        stages = measure_env("BMC_TC_STAGES", 3);
         if (stages != 3 && stages != 4 && stages != 6) stages = 3;
     }
     if (p.n == 128) {
@@ -298,10 +306,11 @@ int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
 int launch_att(const AttParams& p, int impl, cudaStream_t st) {
     if (impl == 1) return launch_att_simt(p, st);
     const int smem = kAttStages * kAttStageBytes + 1024;
-    static bool configured = false;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (!configured) {
         BMC_CUDA(cudaFuncSetAttribute(att_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured = 1;
     }
     dim3 grid((unsigned)p.n_split, (unsigned)p.g.B, (unsigned)p.n_pairs);
     att_tc<<<grid, kThreadsTc, smem, st>>>(p);

@@ -684,7 +684,7 @@ int launch_op(bmc_model* m, const Op& op, cudaStream_t st) {
     if (op.kind == Op::kBieFront) return launch_bie_front(op.fp, st);
     if (op.kind == Op::kFold) {
         static int simt_fold = -1;
-        if (simt_fold < 0) { const char* e = getenv("BMC_FOLD_SIMT"); simt_fold = e ? atoi(e) : 0; }
+        if (simt_fold < 0) simt_fold = measure_env("BMC_FOLD_SIMT", 0);
         return simt_fold ? launch_att_fold(op.dp, st) : launch_att_fold_tc(op.dp, m->map_w128, st);
     }
     return launch_att_softmax(op.sp, st);
@@ -692,7 +692,7 @@ int launch_op(bmc_model* m, const Op& op, cudaStream_t st) {
 
 int run_ops(bmc_model* m, cudaStream_t st) {
     static int want_times = -1;
-    if (want_times < 0) { const char* e = getenv("BMC_OP_TIMES"); want_times = e ? atoi(e) : 0; }
+    if (want_times < 0) want_times = measure_env("BMC_OP_TIMES", 0);
     static int calls = 0;
     if (want_times && ++calls == 4) { want_times = 0; return time_ops(m, st); }
     for (const Op& op : m->ops) {
@@ -740,8 +740,7 @@ extern "C" BMC_EXPORT bmc_model_t* bmc_model_create(int kind, int scale, int n_c
     }
     bmc_model* m = new bmc_model();
     m->kind = kind; m->scale = scale; m->n_c = n_c; m->n_b = n_b; m->repeat = repeat;
-    const char* e = getenv("BMC_NO_GRAPH");
-    m->use_graph = !(e && atoi(e));
+    m->use_graph = !measure_env("BMC_NO_GRAPH", 0);
     register_weights(m);
     return m;
 }
@@ -862,8 +861,7 @@ extern "C" BMC_EXPORT int bmc_model_configure(bmc_model_t* m, int batch, int H, 
         GemmParams probe;
         memset(&probe, 0, sizeof(probe));
         probe.n = 128; probe.n_taps = 9; probe.g = m->g;
-        const char* e = getenv("BMC_FUSED");
-        m->allow_fused = slab_supported(probe) && !(e && !atoi(e));
+        m->allow_fused = slab_supported(probe) && measure_env("BMC_FUSED", 1);
     }
     Builder b{m};
     m->fused = false;
@@ -895,7 +893,7 @@ extern "C" BMC_EXPORT int bmc_model_configure(bmc_model_t* m, int batch, int H, 
         m->off_spart = off; off += align_up((size_t)slots * 2 * 128 * 4, 1024);
     }
     m->ws_bytes = off;
-    m->configured = true;
+    m->configured = 1;
     return BMC_OK;
 }
 
@@ -912,7 +910,11 @@ extern "C" BMC_EXPORT int bmc_model_bind_workspace(bmc_model_t* m, void* workspa
     drop_graph(m);
     m->ws = static_cast<char*>(workspace);
     // halo / tail rows must be zero and are never written with anything else afterwards
+    // (bind has no stream argument: clear on the legacy stream and drain the device, so that kernels later
+    // launched on ANY stream -- including cudaStreamNonBlocking ones, which do not order against the legacy
+    // stream -- see the zeros)
     BMC_CUDA(cudaMemset(m->ws, 0, m->ws_bytes));
+    BMC_CUDA(cudaDeviceSynchronize());
     const uint64_t rows = (uint64_t)m->g.rows();
     int rc = make_tmap_2d_act(&m->map_act, m->slot_ptr(0), rows * m->n_slots, 128, 128, 64);
     if (!rc) rc = make_tmap_2d_act(&m->map_att, m->slot_ptr(0), rows * m->n_slots, 128, 64, 64);

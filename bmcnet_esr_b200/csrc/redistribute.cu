@@ -284,10 +284,11 @@ extern "C" BMC_EXPORT int bmc_stack_to_events(const float* stack, int B, int P, 
     dim3 g2((unsigned)((per_entry + 255) / 256), (unsigned)B);
     redis_expand_kernel<<<g2, 256, 0, st>>>(stack, w.cnt, per_entry, P, C, Y, X, (long)maxlen, rnd, w.sums, w.tmp, w.keys_a, w.idx_a);
     const int smem = 16 * kSortThreads * 4;
-    static bool configured = false;
+    static PerDevice configured_dev;
+    int& configured = configured_dev.cur();
     if (!configured) {
         BMC_CUDA(cudaFuncSetAttribute(redis_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        configured = true;
+        configured = 1;
     }
     redis_sort_kernel<<<B, kSortThreads, smem, st>>>(w.keys_a, w.idx_a, w.keys_b, w.idx_b, w.totals, w.sums, (long)maxlen);
     dim3 g3((unsigned)((maxlen + 255) / 256), (unsigned)B);

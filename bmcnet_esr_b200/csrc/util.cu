@@ -22,21 +22,34 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
 
 bool pdl_enabled() {
     static int on = -1;
-    if (on < 0) { const char* e = getenv("BMC_PDL"); on = e ? atoi(e) : 0; }
+    if (on < 0) on = measure_env("BMC_PDL", 0);
     return on != 0;
 }
 
+int& PerDevice::cur() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
+    return v[dev];
+}
+
 int sm_count() {
-    static int n = 0;
+    static PerDevice cache;
+    int& n = cache.cur();
     if (n == 0) {
-        int dev = 0;
+        int dev = 0, v = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-        cudaDeviceProp p;
-        if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 148;
-        n = p.multiProcessorCount;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 148;
+        n = v;
     }
     return n;
 }
+
+#ifdef BMC_MEASURE
+int measure_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+#endif
 
 // cuTensorMapEncodeTiled is a driver entry point; resolve it through the runtime so the
 // library has no link-time dependency on libcuda (it must load on a GPU-less build host).

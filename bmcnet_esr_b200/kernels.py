@@ -18,27 +18,38 @@ def rows_per_image(h, w):
 
 
 def _need_cuda(*ts):
+    """All operands on ONE CUDA device; returns a context that makes it the current device, so that
+    `stream_ptr()` is that device's current stream and the launch lands there."""
+    dev = None
     for t in ts:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise _lib.BmcError('bmcnet_esr_b200 runs on CUDA tensors only (no CPU fallback); got a %s tensor'
                                 % t.device)
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.BmcError('operands on different devices: %s and %s' % (dev, t.device))
+    return torch.cuda.device(dev)
 
 
 def pack_nchw(x, c_pad=None):
     """fp32 [B,C,H,W] -> padded NHWC act16 [B*R, c_pad] (zero halo)."""
-    _need_cuda(x)
     b, c, h, w = x.shape
     c_pad = c_pad or (c + 63) // 64 * 64
-    out = torch.zeros(b * rows_per_image(h, w), c_pad, dtype=_lib.act_dtype(), device=x.device)
-    x = x.contiguous().float()
-    check(lib().bmc_pack_nchw(x.data_ptr(), b, c, h, w, out.data_ptr(), c_pad, 0, stream_ptr()))
+    with _need_cuda(x):
+        out = torch.zeros(b * rows_per_image(h, w), c_pad, dtype=_lib.act_dtype(), device=x.device)
+        x = x.contiguous().float()
+        check(lib().bmc_pack_nchw(x.data_ptr(), b, c, h, w, out.data_ptr(), c_pad, 0, stream_ptr()))
     return out
 
 
 def unpack_nchw(a, b, c, h, w):
     """padded NHWC act16 [B*R, c_pad] -> fp32 [B,C,H,W]."""
-    out = torch.empty(b, c, h, w, dtype=torch.float32, device=a.device)
-    check(lib().bmc_unpack_nchw(a.data_ptr(), b, c, h, w, a.shape[1], 0, out.data_ptr(), stream_ptr()))
+    with _need_cuda(a):
+        out = torch.empty(b, c, h, w, dtype=torch.float32, device=a.device)
+        check(lib().bmc_unpack_nchw(a.data_ptr(), b, c, h, w, a.shape[1], 0, out.data_ptr(), stream_ptr()))
     return out
 
 
@@ -84,7 +95,8 @@ def conv_gemm(srcs, wpk, bias, b, h, w, taps, n=128, relu=False, residual=None, 
         g, bt = g.contiguous().float(), bt.contiguous().float()
         keep += [g, bt]
         j.ln_gamma = g.data_ptr(); j.ln_beta = bt.data_ptr(); j.ln_eps = eps
-    check(lib().bmc_conv_gemm(C.byref(j), 1, n, taps, b, h, w, impl, stream_ptr()))
+    with _need_cuda(*srcs, wpk, bias, residual):
+        check(lib().bmc_conv_gemm(C.byref(j), 1, n, taps, b, h, w, impl, stream_ptr()))
     return (out, outf) if out_f32 else out
 
 
@@ -93,8 +105,9 @@ def attention_weights(centres, v, b, h, w, scale, n_split=4, impl=0):
     dev = centres.device
     partial = torch.empty(b, n_split, 128, 128, dtype=torch.float32, device=dev)
     probs = torch.empty(b * 256, 64, dtype=_lib.act_dtype(), device=dev)
-    check(lib().bmc_attention_weights(centres.data_ptr(), v.data_ptr(), b, h, w, scale, partial.data_ptr(),
-                                      n_split, probs.data_ptr(), impl, stream_ptr()))
+    with _need_cuda(centres, v):
+        check(lib().bmc_attention_weights(centres.data_ptr(), v.data_ptr(), b, h, w, scale, partial.data_ptr(),
+                                          n_split, probs.data_ptr(), impl, stream_ptr()))
     return probs, partial
 
 
@@ -108,13 +121,15 @@ def apply_dynamic_weights(v, probs, b, h, w, residual=None, impl=0):
     j.w = probs.data_ptr(); j.w_rows = 128; j.w_k = 128; j.w_row_base = 0; j.w_img_stride = 256
     j.residual = residual.data_ptr() if residual is not None else None
     j.out_act16 = out.data_ptr()
-    check(lib().bmc_conv_gemm(C.byref(j), 1, 128, 1, b, h, w, impl, stream_ptr()))
+    with _need_cuda(v, probs, residual):
+        check(lib().bmc_conv_gemm(C.byref(j), 1, 128, 1, b, h, w, impl, stream_ptr()))
     return out
 
 
 def layernorm_rows(a, gamma, beta, eps):
     out = torch.empty_like(a)
     g, bt = gamma.contiguous().float(), beta.contiguous().float()
-    check(lib().bmc_layernorm_rows(a.data_ptr(), g.data_ptr(), bt.data_ptr(), eps, a.shape[0], out.data_ptr(),
-                                   stream_ptr()))
+    with _need_cuda(a, g, bt):
+        check(lib().bmc_layernorm_rows(a.data_ptr(), g.data_ptr(), bt.data_ptr(), eps, a.shape[0], out.data_ptr(),
+                                       stream_ptr()))
     return out

@@ -35,22 +35,28 @@ def _models():
 
 
 def _check_step(got, ref, x, tag):
-    """got / ref: [hiddens..., x_o]."""
+    """got / ref: [hiddens..., x_o].  Returns the measured errors (for the error-vs-step curves)."""
     o, ro = got[-1].cpu(), ref[-1]
     err = (o - ro).abs().max().item()
     assert err <= ABS_TOL, (tag, 'x_o max-abs', err)
     up = F.interpolate(x[:, :, 1], scale_factor=4, mode='bilinear', align_corners=False)
     res = (ro - up).abs().max().item()
-    assert err <= REL_TOL * max(res, 1e-3) or err <= 2e-4, (tag, 'residual-relative', err, res)
+    # the learned residual must be resolved to 1 % of its own size; weights with a residual below 0.02 would make
+    # this bar tighter than fp16 storage of the O(1) prediction allows (2^-11 relative), hence the floor
+    assert err <= REL_TOL * max(res, 0.02), (tag, 'residual-relative', err, res)
     gt = torch.poisson(F.interpolate(x[:, :, 1], scale_factor=4, mode='nearest') / 16 + 0.05,
                        generator=torch.Generator().manual_seed(1))
-    assert abs(_psnr(o, gt) - _psnr(ro, gt)) <= PSNR_TOL_DB, (tag, 'psnr')
+    dpsnr = abs(_psnr(o, gt) - _psnr(ro, gt))
+    assert dpsnr <= PSNR_TOL_DB, (tag, 'psnr')
+    hid = []
     for i, (h, rh) in enumerate(zip(got[:-1], ref[:-1])):
         e = (h.cpu() - rh).abs().max().item()
         assert e <= REL_TOL * rh.abs().max().item(), (tag, 'hidden %d' % i, e, rh.abs().max().item())
+        hid.append(e / rh.abs().max().item())
+    return {'x_o_max_abs': err, 'residual_max_abs': res, 'psnr_diff_db': dpsnr, 'hidden_rel': hid}
 
 
-def _rollout(model, fwd, sd, b, h, w, steps, seed, tag, transposed_input=False):
+def _rollout(model, fwd, sd, b, h, w, steps, seed, tag, transposed_input=False, curve=None):
     n_state = 2 if fwd is O.bmcnet_plain_forward else 4
     ref = [torch.zeros(b, 128, h, w) for _ in range(n_state - 1)] + [torch.zeros(b, 32, h, w)]
     got = [t.cuda() for t in ref]
@@ -64,8 +70,23 @@ def _rollout(model, fwd, sd, b, h, w, steps, seed, tag, transposed_input=False):
             assert not xg.is_contiguous()
         got = list(model(xg, *got, init))
         init = False
-        _check_step(got, ref, x, '%s step %d' % (tag, s))
+        m = _check_step(got, ref, x, '%s step %d' % (tag, s))
+        if curve is not None:
+            curve.append(dict(m, step=s))
     return got, ref
+
+
+def _save_curve(name, curve):
+    """Error-vs-step curves of the long rollouts: written to gpurun_out/ on the GPU box (merged back by gpurun),
+    summarised in profiles/r02_rollout_error.md."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    try:
+        os.makedirs(d, exist_ok=True)
+        with open(os.path.join(d, 'rollout_error_%s.json' % name), 'w') as f:
+            json.dump(curve, f)
+    except OSError:
+        pass
 
 
 def test_plain_shipped_checkpoint_nfs_shape(plain_ckpt):
@@ -266,3 +287,80 @@ def test_bmcnet_sequences_independent_many_tiles(plain_ckpt):
         ref = list(O.bmcnet_forward(sd, x[20:21].cpu(), *ref, init))
         init = False
     _check_step([t[20:21] for t in full], ref, xs[-1][20:21].cpu(), 'bmcnet B=38 seq 20')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Long rollouts ("S >= 16 for parity"; infer_BMCNet.py:46-68 carries the state over a whole recording):
+# the hidden state is stored in fp16 between steps and every step runs 5 (plain) / 15 (BMCNet) softmaxes, which is
+# where slow drift would hide.  All bars are asserted at EVERY one of the 32 steps.
+LONG_STEPS = 32
+
+
+def test_long_rollout_plain_shipped_nfs(plain_ckpt):
+    _, BMCNet_plain = _models()
+    m = BMCNet_plain(4, 128, 5)
+    m.load_state_dict(plain_ckpt, strict=True)
+    m = m.cuda().eval()
+    curve = []
+    _rollout(m, O.bmcnet_plain_forward, plain_ckpt, 1, 45, 80, LONG_STEPS, 5000, 'plain/shipped/45x80/S32',
+             transposed_input=True, curve=curve)
+    _save_curve('plain_shipped_45x80', curve)
+
+
+@pytest.mark.parametrize('h,w', [(45, 80), (31, 56)])
+def test_long_rollout_bmcnet_transplant(plain_ckpt, h, w):
+    BMCNet, _ = _models()
+    sd = O.surrogate_state_dict(plain=False, seed=7, transplant=plain_ckpt)
+    m = BMCNet(4, 128, 5)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    curve = []
+    _rollout(m, O.bmcnet_forward, sd, 1, h, w, LONG_STEPS, 6000 + h, 'bmcnet/transplant/%dx%d/S32' % (h, w),
+             transposed_input=True, curve=curve)
+    _save_curve('bmcnet_transplant_%dx%d' % (h, w), curve)
+
+
+@pytest.mark.parametrize('kind,b,h,w', [('plain', 95, 45, 80), ('full', 76, 45, 80), ('full', 156, 31, 56)])
+def test_bench_batch_sequences_vs_oracle(plain_ckpt, kind, b, h, w):
+    """The batches bench.py runs (plain B=95, BMCNet B=76 / 156): three sequences of the batch -- first, middle,
+    last -- against the fp32 oracle over 4 recurrent steps, every bar at every step."""
+    BMCNet, BMCNet_plain = _models()
+    if kind == 'plain':
+        cls, sd, fwd, n_state = BMCNet_plain, plain_ckpt, O.bmcnet_plain_forward, 2
+    else:
+        cls, fwd, n_state = BMCNet, O.bmcnet_forward, 4
+        sd = O.surrogate_state_dict(plain=False, transplant=plain_ckpt)
+    m = cls(4, 128, 5)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    picks = [0, b // 2, b - 1]
+    steps = 4
+    xs = [synth_counts(b, h, w, 7000 + s) for s in range(steps)]
+    st = [torch.zeros(b, 128, h, w).cuda() for _ in range(n_state - 1)] + [torch.zeros(b, 32, h, w).cuda()]
+    ref = [torch.zeros(len(picks), 128, h, w) for _ in range(n_state - 1)] + [torch.zeros(len(picks), 32, h, w)]
+    for s, x in enumerate(xs):
+        st = list(m(x.cuda(), *st, s == 0))
+        ref = list(fwd(sd, x[picks], *ref, s == 0))
+        _check_step([t[picks] for t in st], ref, x[picks], '%s B=%d step %d' % (kind, b, s))
+
+
+def test_forward_is_bit_reproducible(plain_ckpt):
+    """Two runs of the same rollout give bit-identical outputs: the attention partial sums are reduced in a fixed
+    order (att_fold sums the per-CTA slots in slot order), nothing in the model path uses float atomics."""
+    BMCNet, _ = _models()
+    sd = O.surrogate_state_dict(plain=False, transplant=plain_ckpt)
+    m = BMCNet(4, 128, 5)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    b, h, w = 5, 45, 80
+    xs = [synth_counts(b, h, w, 8000 + s).cuda() for s in range(3)]
+
+    def run():
+        st = [torch.zeros(b, 128, h, w).cuda() for _ in range(3)] + [torch.zeros(b, 32, h, w).cuda()]
+        for s, x in enumerate(xs):
+            st = list(m(x, *st, s == 0))
+        return [t.clone() for t in st]
+
+    a, c = run(), run()
+    for t, u in zip(a, c):
+        assert torch.equal(t, u)

@@ -1,4 +1,6 @@
 #!/bin/bash
+# the BMC_* switches below exist only in the measurement library (python -m bmcnet_esr_b200.build --measure)
+export BMC_B200_LIB=${BMC_B200_LIB:-$PWD/bmcnet_esr_b200/libbmc_b200_measure.so}
 # ncu evidence: per-launch device times of whole steps (bench batch sizes), full captures of the
 # kernels that dominate a step, per-op CUDA-event timings.  Text summaries under gpurun_out/prof/.
 mkdir -p gpurun_out/prof

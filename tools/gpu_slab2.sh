@@ -1,4 +1,6 @@
 #!/bin/bash
+# the BMC_* switches below exist only in the measurement library (python -m bmcnet_esr_b200.build --measure)
+export BMC_B200_LIB=${BMC_B200_LIB:-$PWD/bmcnet_esr_b200/libbmc_b200_measure.so}
 # A/B of the slab convolution kernels: parity tests, per-launch timing, bench lines, per-op timings.
 mkdir -p gpurun_out
 timeout 600 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py tests/test_gpu_metrics.py -x -q > gpurun_out/pytest_slab2.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_slab2.log
