@@ -59,6 +59,10 @@ SIGNATURES = {
     'bmc_stack_to_events': (_i, [_vp, _i, _i, _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     'bmc_stack2cnt': (_i, [_vp, _i, _i, _i, _i, _vp, _vp]),
     'bmc_sr_metrics': (_i, [_vp, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp, _vp]),
+    'bmc_conv_wgrad_workspace_bytes': (_sz, [_i, _i, _i]),
+    'bmc_conv_wgrad': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
+    'bmc_relu_backward': (_i, [_vp, _vp, _i64, _vp, _vp]),
+    'bmc_adam_amsgrad_step': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _f, _f, _f, _f, _vp]),
 }
 
 _lib = None

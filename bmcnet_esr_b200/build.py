@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libbmc_b200.so')
-SOURCES = ['util.cu', 'encode.cu', 'gemm_tc.cu', 'gemm_slab.cu', 'gemm_slabt.cu', 'gemm_slab2.cu', 'bie_fused.cu', 'gemm_simt.cu', 'pointwise.cu', 'eval_tail.cu', 'redistribute.cu', 'model.cu']
+SOURCES = ['util.cu', 'encode.cu', 'gemm_tc.cu', 'gemm_slab.cu', 'gemm_slabt.cu', 'gemm_slab2.cu', 'bie_fused.cu', 'gemm_simt.cu', 'pointwise.cu', 'eval_tail.cu', 'redistribute.cu', 'train.cu', 'model.cu']
 HEADERS = ['common.cuh', 'gemm.cuh', 'gemm_epi.cuh', os.path.join('..', '..', 'include', 'bmc_b200.h')]
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden']

@@ -133,3 +133,21 @@ def layernorm_rows(a, gamma, beta, eps):
         check(lib().bmc_layernorm_rows(a.data_ptr(), g.data_ptr(), bt.data_ptr(), eps, a.shape[0], out.data_ptr(),
                                        stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------------ training kernels
+def relu_backward(dy, y):
+    """dx = dy * (y > 0) on act16 tensors (bmc_relu_backward)."""
+    dx = torch.empty_like(dy)
+    with _need_cuda(dy, y):
+        check(lib().bmc_relu_backward(dy.data_ptr(), y.data_ptr(), dy.numel(), dx.data_ptr(), stream_ptr()))
+    return dx
+
+
+def conv_wgrad(dy, x, taps, b, h, w, cmap, cin_total, n_out, scale, grad_w, grad_b, workspace, n_split):
+    """grad_w[co][cmap[ci]][tap] += scale * sum_rows dy[row][co] * x[row + off_tap][ci] (and grad_b += scale * column
+    sums of dy when given): bmc_conv_wgrad.  dy: act16 [B*R,128]; x: act16 [B*R, 64|128]; cmap: int32 [x_ch]."""
+    with _need_cuda(dy, x, cmap, grad_w, grad_b, workspace):
+        check(lib().bmc_conv_wgrad(dy.data_ptr(), x.data_ptr(), x.shape[1], taps, b, h, w, cmap.data_ptr(), cin_total,
+                                   n_out, scale, grad_w.data_ptr(), grad_b.data_ptr() if grad_b is not None else None,
+                                   workspace.data_ptr(), workspace.numel(), n_split, stream_ptr()))

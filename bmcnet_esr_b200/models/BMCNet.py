@@ -7,6 +7,7 @@ into libbmc_b200 (bmc_model_forward).
 import torch
 import torch.nn as nn
 
+from . import _train
 from ._engine import Engine
 from .submodules import BIE, PixelUnShuffle, ResidualBlock_noBN, initialize_weights
 from .._lib import MODEL_BMCNET
@@ -55,13 +56,15 @@ class BMCNet(nn.Module):
         self.down = PixelUnShuffle(scale)
         self.repeat = repeat
         self._engine = Engine(MODEL_BMCNET, scale, n_c, n_b, repeat)
+        self.loss_scale = _train.DEFAULT_LOSS_SCALE      # static fp16 loss scale of the training path (models/_train.py)
 
     def forward(self, x, x_h, x_h_p, x_h_n, x_o, init):
         """Same arguments and return order as the reference (BMCNet.py:95-121):
         (x_h, x_h_p, x_h_n, x_o), x_o = [B,2,sH,sW].  The reference hands (x_h, x_h_p, x_h_n)
         positionally to Backbone.forward(xs, hp, hn, hs, o); that pairing is reproduced."""
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError('bmcnet_esr_b200 implements the inference path; call .eval() / no_grad')
+        if _train.route(self, x, x_h, x_h_p, x_h_n, x_o):
+            # train() mode with autograd recording (train.py:192,202-237): kernels behind autograd Functions
+            return _train.forward_full(self, _train.context(self), x, x_h, x_h_p, x_h_n, x_o, init)
         with torch.no_grad():
             (h, hp, hn), o = self._engine.forward(self, x, [x_h, x_h_p, x_h_n], x_o, init)
         return h, hp, hn, o

@@ -1,12 +1,13 @@
 """BMCNet_plain -- drop-in for the reference `models/BMCNet_plain.py` (:3-68).
 
 Same constructor, forward signature and state_dict keys (120, with the reference's aliasing);
-the forward pass is one call into libbmc_b200 (bmc_model_forward): NHWC bf16 tcgen05 kernels
+the forward pass is one call into libbmc_b200 (bmc_model_forward): NHWC fp16 (default build) tcgen05 kernels
 with fp32 accumulation, one CUDA graph per step.
 """
 import torch
 import torch.nn as nn
 
+from . import _train
 from ._engine import Engine
 from .submodules import BIE, PixelUnShuffle, initialize_weights
 from .._lib import MODEL_BMCNET_PLAIN
@@ -36,12 +37,14 @@ class BMCNet_plain(nn.Module):
         self.down = PixelUnShuffle(scale)
         self.repeat = repeat
         self._engine = Engine(MODEL_BMCNET_PLAIN, scale, n_c, n_b, repeat)
+        self.loss_scale = _train.DEFAULT_LOSS_SCALE      # static fp16 loss scale of the training path (models/_train.py)
 
     def forward(self, x, x_h, x_o, init):
         """x [B,2,T,H,W] counts (frames 0,1 used); x_h [B,n_c,H,W]; x_o [B,2*scale^2,H,W] when
         `init` else the previous [B,2,sH,sW] output.  Returns (x_h, x_o) like the reference."""
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError('bmcnet_esr_b200 implements the inference path; call .eval() / no_grad')
+        if _train.route(self, x, x_h, x_o):
+            # train() mode with autograd recording (train_plain.py:151): kernels behind autograd Functions
+            return _train.forward_plain(self, _train.context(self), x, x_h, x_o, init)
         with torch.no_grad():
             (h,), o = self._engine.forward(self, x, [x_h], x_o, init)
         return h, o

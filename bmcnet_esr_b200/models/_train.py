@@ -1,0 +1,449 @@
+"""Training path of BMCNet / BMCNet_plain (reference train.py:202-237).
+
+The reference trains with plain autograd over its nn.Modules: forward over a sequence of window pairs with the
+state carried (no detach -> BPTT), `loss += MSELoss(pred, gt)`, one `loss.backward()`, one Adam(amsgrad) step.
+Here the SAME user code works (`model.train()`, the loop, `loss.backward()`, any torch optimiser): when autograd
+is recording, `BMCNet.forward` / `BMCNet_plain.forward` route to this module, which builds the graph out of
+`torch.autograd.Function`s whose forward AND backward are the sm_100a kernels of libbmc_b200:
+
+  every convolution (216 per BMCNet step, 99.5 % of the FLOPs; BMCNet.py:40-53, submodules.py:25-26,44-53)
+      forward   bmc_conv_gemm (the tcgen05 slab / per-tap kernels, K segments = torch.cat inputs, bias + ReLU fused)
+      dgrad     bmc_conv_gemm again: dY convolved with the spatially mirrored, channel-transposed weights
+      wgrad     bmc_conv_wgrad (csrc/train.cu: tcgen05 split-K over pixels, fp32, accumulated straight into
+                `param.grad` -- aliased modules share one Parameter, hence one gradient buffer)
+      ReLU'     bmc_relu_backward
+  the small rest (channel LayerNorm, the 128x128 attention bmm/softmax, residual adds, pixel (un)shuffle, bilinear
+  base, MSE) is ordinary differentiable PyTorch on the padded-NHWC tensors, in fp32 where it matters.
+
+Activations and activation gradients are act16 (fp16 in the default build); weight gradients accumulate in fp32.
+fp16 gradients of a mean-reduced MSE over 10^5 outputs (~1e-6) would underflow, so the whole 16-bit region runs under a
+STATIC loss scale that never leaves this module: gradients are multiplied by `loss_scale` where they enter (the
+prediction / state outputs) and divided where they leave (wgrad's `scale`, the LayerNorm parameters, the state
+inputs), so `loss.backward()` on the user's unscaled loss yields unscaled `param.grad`.
+
+Also here: FusedAdamAMSGrad (bmc_adam_amsgrad_step over one flat fp32 buffer) and allreduce_gradients (the one
+collective of the data-parallel training step: a single NCCL all-reduce of the 2,731,680 alias-deduplicated
+gradients).
+"""
+import ctypes as C
+
+import torch
+import torch.nn.functional as F
+
+from .. import _lib, kernels as K
+from .._lib import check, lib, stream_ptr
+
+WGRAD_SPLITS = 16
+DEFAULT_LOSS_SCALE = 2.0 ** 14
+
+
+# ------------------------------------------------------------------------------------------ layout (differentiable)
+def to_packed(x, c_pad):
+    """fp32 NCHW [B,C,H,W] -> padded NHWC act16 [B*R, c_pad] with zero halo, built from differentiable torch ops."""
+    b, c, h, w = x.shape
+    r = K.rows_per_image(h, w)
+    y = F.pad(x, (1, 1, 1, 1)).permute(0, 2, 3, 1).reshape(b, (h + 2) * (w + 2), c)
+    y = F.pad(y, (0, c_pad - c, 0, r - (h + 2) * (w + 2)))
+    return y.reshape(b * r, c_pad).to(_lib.act_dtype())
+
+
+def from_packed(a, b, c, h, w):
+    """padded NHWC act16 [B*R, c_pad] -> fp32 NCHW [B,C,H,W] (differentiable)."""
+    r = K.rows_per_image(h, w)
+    y = a.view(b, r, a.shape[1])[:, :(h + 2) * (w + 2), :c].reshape(b, h + 2, w + 2, c)
+    return y[:, 1:h + 1, 1:w + 1].permute(0, 3, 1, 2).float()
+
+
+class _ScaleGrad(torch.autograd.Function):
+    """identity forward; backward multiplies the gradient by a constant (loss-scale boundaries)."""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.s = s
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g * ctx.s, None
+
+
+# ------------------------------------------------------------------------------------------ convolution
+class _Ctx:
+    """Per-model training context: geometry-independent caches (packed weights by parameter version, channel
+    maps, wgrad workspace) and the loss scale."""
+
+    def __init__(self, loss_scale):
+        self.loss_scale = float(loss_scale)
+        self.wcache = {}
+        self.cmaps = {}
+        self.ws = None
+
+    def workspace(self, dev):
+        nbytes = lib().bmc_conv_wgrad_workspace_bytes(WGRAD_SPLITS, 9, 128)
+        if self.ws is None or self.ws.device != dev:
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        return self.ws
+
+    def cmap(self, idx, dev):
+        key = (tuple(idx), str(dev))
+        if key not in self.cmaps:
+            self.cmaps[key] = torch.tensor(idx, dtype=torch.int32, device=dev)
+        return self.cmaps[key]
+
+    def packed_weight(self, weight, segs, mode, seg=None):
+        """mode 'fwd': chunk-major forward weights for the K segments `segs` (lists of weight input channels, -1 =
+        padding), output channels zero-padded to 128.  mode 'bwd': the data-gradient weights of segment `seg`:
+        out = its (padded) input channels, in = the 128 (padded) output channels, taps mirrored."""
+        key = (id(weight), weight._version, tuple(map(tuple, segs)), mode, seg)
+        hit = self.wcache.get(key)
+        if hit is not None:
+            return hit
+        w = weight.detach().float()
+        n, cin, kh, kw = w.shape
+        if n < 128:
+            w = F.pad(w, (0, 0, 0, 0, 0, 0, 0, 128 - n))
+        if mode == 'fwd':
+            cols = []
+            for idx in segs:
+                it = torch.tensor(idx, device=w.device)
+                ws = w.index_select(1, it.clamp(min=0)) * (it >= 0).view(1, -1, 1, 1)
+                cols.append(ws.reshape(128, len(idx), kh * kw).permute(0, 2, 1).reshape(128, -1))     # [N, taps*c]
+            wk = torch.cat(cols, 1)
+        else:
+            idx = segs[seg]
+            it = torch.tensor(idx, device=w.device)
+            ws = w.index_select(1, it.clamp(min=0)) * (it >= 0).view(1, -1, 1, 1)                      # [128 co, c, kh, kw]
+            wt = ws.permute(1, 0, 2, 3).flip(2, 3)                                                    # [c, 128 co, kh, kw] mirrored
+            c = len(idx)
+            if c < 128:
+                wt = F.pad(wt, (0, 0, 0, 0, 0, 0, 0, 128 - c))
+            wk = wt.reshape(128, 128, kh * kw).permute(0, 2, 1).reshape(128, -1)
+        k = wk.shape[1]
+        out = wk.reshape(128, k // 64, 64).permute(1, 0, 2).contiguous().to(_lib.act_dtype())
+        self.wcache[key] = out
+        return out
+
+
+def _grad_buf(p):
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class _ConvFn(torch.autograd.Function):
+    """`weight` is passed as a tensor input only so that autograd sees the dependence on the parameters (the very
+    first convolutions of a sequence have no other input that requires grad); its gradient -- and the bias's --
+    is accumulated into `.grad` by the wgrad kernel, so backward returns None for it."""
+
+    @staticmethod
+    def forward(ctx, weight, tc, conv, segs, relu, use_bias, geom, *srcs):
+        b, h, w = geom
+        taps = conv.kernel_size[0] * conv.kernel_size[1]
+        n_out = conv.out_channels
+        wpk = tc.packed_weight(conv.weight, segs, 'fwd')
+        bias = None
+        if use_bias:
+            bias = conv.bias.detach().float()
+            if n_out < 128:
+                bias = F.pad(bias, (0, 128 - n_out))
+        srcs = [s.contiguous() for s in srcs]
+        out = K.conv_gemm(srcs, wpk, bias, b, h, w, taps, n=128, relu=relu)
+        ctx.tc, ctx.conv, ctx.segs, ctx.relu, ctx.geom, ctx.taps, ctx.use_bias = tc, conv, segs, relu, geom, taps, use_bias
+        ctx.save_for_backward(out if relu else None, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tc, conv, segs, geom, taps = ctx.tc, ctx.conv, ctx.segs, ctx.geom, ctx.taps
+        b, h, w = geom
+        out, *srcs = ctx.saved_tensors
+        dz = dout.contiguous()
+        dev = dz.device
+        if ctx.relu:
+            dz = K.relu_backward(dz, out)
+        ws = tc.workspace(dev)
+        gw = _grad_buf(conv.weight)
+        gb = _grad_buf(conv.bias)
+        inv = 1.0 / tc.loss_scale
+        for i, (src, idx) in enumerate(zip(srcs, segs)):
+            K.conv_wgrad(dz, src, taps, b, h, w, tc.cmap(idx, dev), conv.in_channels, conv.out_channels, inv,
+                         gw, gb if (i == 0 and ctx.use_bias) else None, ws, WGRAD_SPLITS)
+        grads = []
+        for i, src in enumerate(srcs):
+            if not ctx.needs_input_grad[7 + i]:
+                grads.append(None)
+                continue
+            wt = tc.packed_weight(conv.weight, segs, 'bwd', i)
+            g = K.conv_gemm([dz], wt, None, b, h, w, taps, n=128)
+            grads.append(g if src.shape[1] == 128 else g[:, :src.shape[1]].contiguous())
+        return (None, None, None, None, None, None, None, *grads)
+
+
+def conv(tc, module, srcs, segs, geom, relu=False):
+    """module(cat(srcs)) on packed act16 sources; segs[i] lists, per channel of source i, the input channel of
+    `module.weight` it multiplies (-1 for padding channels).  bmc_conv_gemm takes up to 3 sources per job: a wider
+    concatenation (conv_fs of BMCNet: 4) is the sum of two launches, bias in the first, ReLU after the sum."""
+    if len(srcs) <= 3:
+        return _ConvFn.apply(module.weight, tc, module, segs, relu, True, geom, *srcs)
+    a = _ConvFn.apply(module.weight, tc, module, segs[:3], False, True, geom, *srcs[:3])
+    c = _ConvFn.apply(module.weight, tc, module, segs[3:], False, False, geom, *srcs[3:])
+    out = a + c
+    return F.relu(out) if relu else out
+
+
+_R128 = list(range(128))
+
+
+def _seg(first, count=128, pad_to=128):
+    return list(range(first, first + count)) + [-1] * (pad_to - count)
+
+
+# ------------------------------------------------------------------------------------------ blocks
+def resblock(tc, m, x, geom):
+    """ResidualBlock_noBN (submodules.py:31-35)."""
+    t = conv(tc, m.conv1, [x], [_R128], geom, relu=True)
+    return x + conv(tc, m.conv2, [t], [_R128], geom)
+
+
+def layernorm_rows(y, weight, bias, eps):
+    """LayerNorm2d over channels on packed rows (submodules.py:127-139), fp32 math."""
+    yf = y.float()
+    mu = yf.mean(1, keepdim=True)
+    d = yf - mu
+    var = (d * d).mean(1, keepdim=True)
+    return (weight.view(1, -1) * (d / (var + eps).sqrt()) + bias.view(1, -1)).to(y.dtype)
+
+
+def bie(tc, m, x1, x2, xs, geom):
+    """BIE.forward (submodules.py:58-77) on packed tensors."""
+    b, h, w = geom
+    r = K.rows_per_image(h, w)
+    r1 = resblock(tc, m.conv1, x1, geom)
+    r2 = resblock(tc, m.conv2, x2, geom)
+    s = 1.0 / tc.loss_scale
+    gamma, beta = _ScaleGrad.apply(m.norm_s.weight, s), _ScaleGrad.apply(m.norm_s.bias, s)
+    two = [_R128, _seg(128)]
+
+    def centre(convf, other):
+        u = conv(tc, convf, [xs, other], two, geom)
+        return conv(tc, m.clustering, [layernorm_rows(u, gamma, beta, m.norm_s.eps)], [_R128], geom)
+
+    c1, c2 = centre(m.convf1, x2), centre(m.convf2, x1)
+    v1 = conv(tc, m.v1, [x1], [_R128], geom)
+    v2 = conv(tc, m.v2, [x2], [_R128], geom)
+
+    def attend(c, v):
+        cf, vf = c.view(b, r, 128).float(), v.view(b, r, 128).float()
+        att = torch.bmm(cf.transpose(1, 2), vf) * m.scale                 # [b, c, c'] = centres . v^T (:69-70)
+        p = torch.softmax(att, -1)
+        return torch.bmm(vf, p.transpose(1, 2)).reshape(b * r, 128).to(c.dtype)     # (P v)^T in row layout (:72-73)
+
+    o1, o2 = attend(c1, v1), attend(c2, v2)
+    ns = conv(tc, m.unclustering, [c1, c2], two, geom) + xs
+    return o1 + r2, o2 + r1, ns
+
+
+def _planes(x, repeat):
+    f1, f2 = x[:, :, 0], x[:, :, 1]
+    rep = lambda t: t.repeat(1, repeat, 1, 1)
+    return f2, rep(f1[:, 0:1]), rep(f1[:, 1:2]), rep(f2[:, 0:1]), rep(f2[:, 1:2])
+
+
+def _reconstruct(a_o, f2, geom, scale):
+    b, h, w = geom
+    n_o = from_packed(a_o, b, 2 * scale * scale, h, w)
+    return F.pixel_shuffle(n_o, scale) + F.interpolate(f2[:, :2].float(), scale_factor=scale, mode='bilinear',
+                                                       align_corners=False)
+
+
+def _state_in(t, tc):
+    return to_packed(_ScaleGrad.apply(t.float(), 1.0 / tc.loss_scale), 128)
+
+
+def _state_out(a, geom, tc):
+    b, h, w = geom
+    return _ScaleGrad.apply(from_packed(a, b, 128, h, w), tc.loss_scale)
+
+
+def forward_plain(model, tc, x, x_h, x_o, init):
+    """BMCNet_plain.forward (BMCNet_plain.py:44-68) with autograd."""
+    nb = model.neuro
+    b, _, _, h, w = x.shape
+    geom = (b, h, w)
+    sc, rp = model.scale, model.repeat
+    k = sc * sc
+    x = x.float()
+    f2, x1p, x1n, x2p, x2n = _planes(x, rp)
+    o = x_o.float() if init else F.pixel_unshuffle(x_o.float(), sc)
+    o = _ScaleGrad.apply(o, 1.0 / tc.loss_scale)
+    hs = _state_in(x_h, tc)
+    in_1, in_2 = torch.cat([x1p, x2p], 1), torch.cat([x1n, x2n], 1)
+    n6 = 2 * rp
+    # conv_f1(cat[in_1(6), h(128), o1(16)]): sources = h and the packed small planes
+    m1 = to_packed(torch.cat([in_1, o[:, :k]], 1), 64)
+    m2 = to_packed(torch.cat([in_2, o[:, k:]], 1), 64)
+    ms = to_packed(torch.cat([in_1, in_2, o], 1), 64)
+    seg_small = _seg(0, n6, 0) + list(range(n6 + 128, n6 + 128 + k))
+    seg_small += [-1] * (64 - len(seg_small))
+    x1 = conv(tc, nb.conv_f1, [hs, m1], [_seg(n6), seg_small], geom, relu=True)
+    x2 = conv(tc, nb.conv_f2, [hs, m2], [_seg(n6), seg_small], geom, relu=True)
+    seg_s = list(range(2 * n6)) + list(range(2 * n6 + 128, 2 * n6 + 128 + 2 * k))
+    seg_s += [-1] * (64 - len(seg_s))
+    xs = conv(tc, nb.conv_fs, [hs, ms], [_seg(2 * n6), seg_s], geom, relu=True)
+    for blk in nb.para_reschunk:
+        x1, x2, xs = bie(tc, blk, x1, x2, xs, geom)
+    n_h = conv(tc, nb.conv_h, [xs], [_R128], geom, relu=True)
+    a_o = conv(tc, nb.conv_o, [x1, x2], [_R128, _seg(128)], geom)
+    pred = _reconstruct(_ScaleGrad.apply(a_o, tc.loss_scale), f2, geom, sc)
+    return _state_out(n_h, geom, tc), pred
+
+
+def forward_full(model, tc, x, x_h, x_h_p, x_h_n, x_o, init):
+    """BMCNet.forward (BMCNet.py:95-121) + Backbone.forward (:57-84) + ParallelBlk.forward (:19-32) with autograd."""
+    nb = model.neuro
+    b, _, _, h, w = x.shape
+    geom = (b, h, w)
+    sc, rp = model.scale, model.repeat
+    k = sc * sc
+    x = x.float()
+    f2, x1p, x1n, x2p, x2n = _planes(x, rp)
+    o = x_o.float() if init else F.pixel_unshuffle(x_o.float(), sc)
+    o = _ScaleGrad.apply(o, 1.0 / tc.loss_scale)
+    # positional hand-over of the reference: Backbone.forward(xs, hp, hn, hs, o) is called with (x_h, x_h_p, x_h_n)
+    hp, hn, hs = _state_in(x_h, tc), _state_in(x_h_p, tc), _state_in(x_h_n, tc)
+    n6 = 2 * rp
+    mp = to_packed(torch.cat([x1p, x2p, o[:, :k]], 1), 64)           # conv_fpst: cat[xp(6), hp, op(16)]
+    mn = to_packed(torch.cat([x1n, x2n, o[:, k:]], 1), 64)
+    seg_small = _seg(0, n6, 0) + list(range(n6 + 128, n6 + 128 + k))
+    seg_small += [-1] * (64 - len(seg_small))
+    xp_st = conv(tc, nb.conv_fpst, [hp, mp], [_seg(n6), seg_small], geom, relu=True)
+    xn_st = conv(tc, nb.conv_fnst, [hn, mn], [_seg(n6), seg_small], geom, relu=True)
+    m2p, m2n = to_packed(x2p, 64), to_packed(x2n, 64)               # conv_fps: cat[x2p(3), hp]
+    seg3 = _seg(0, rp, 64)
+    xp_s = conv(tc, nb.conv_fps, [hp, m2p], [_seg(rp), seg3], geom, relu=True)
+    xn_s = conv(tc, nb.conv_fns, [hn, m2n], [_seg(rp), seg3], geom, relu=True)
+    mo = to_packed(o, 64)                                           # conv_fs: cat[xp_st, xn_st, h*, o(32)]
+    seg_o = _seg(384, 2 * k, 64)
+    fs = lambda hx: conv(tc, nb.conv_fs, [xp_st, xn_st, hx, mo], [_R128, _seg(128), _seg(256), seg_o], geom, relu=True)
+    xs, xs_p, xs_n = fs(hs), fs(hp), fs(hn)
+    for blk in nb.para_reschunk:
+        xp_s = resblock(tc, blk.conv1, xp_s, geom)
+        xn_s = resblock(tc, blk.conv2, xn_s, geom)
+        xp_st = resblock(tc, blk.conv1_st, xp_st, geom)
+        xn_st = resblock(tc, blk.conv2_st, xn_st, geom)
+        xp_s, xp_st, xs_p = bie(tc, blk.lBIE, xp_s, xp_st, xs_p, geom)
+        xn_s, xn_st, xs_n = bie(tc, blk.lBIE, xn_s, xn_st, xs_n, geom)
+        xp_s, xn_s, xs = bie(tc, blk.gBIE, xp_s, xn_s, xs, geom)
+    n_h = conv(tc, nb.conv_hs, [xs], [_R128], geom, relu=True)
+    n_hp = conv(tc, nb.conv_hp, [xs_p], [_R128], geom, relu=True)
+    n_hn = conv(tc, nb.conv_hn, [xs_n], [_R128], geom, relu=True)
+    a_o = conv(tc, nb.conv_o, [xp_s, xn_s], [_R128, _seg(128)], geom)
+    pred = _reconstruct(_ScaleGrad.apply(a_o, tc.loss_scale), f2, geom, sc)
+    return _state_out(n_h, geom, tc), _state_out(n_hp, geom, tc), _state_out(n_hn, geom, tc), pred
+
+
+_warned_eval_grad = False
+
+
+def route(model, *tensors):
+    """True when this call must record an autograd graph: `model.train()` (train.py:192) with grad mode on.
+    In eval() mode the inference kernels run and the outputs carry no grad_fn -- what the reference's own
+    inference / validation code asks for (`@torch.no_grad()`, infer_BMCNet.py:144; train.py:476).  A caller who
+    left grad mode on in eval() is told once; an INPUT that requires grad cannot be honoured there and raises."""
+    global _warned_eval_grad
+    if not torch.is_grad_enabled():
+        return False
+    if model.training:
+        return True
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise _lib.BmcError('an input requires grad but the module is in eval() mode: the inference kernels record no '
+                            'autograd graph; call .train() for the differentiable path')
+    if not _warned_eval_grad and any(p.requires_grad for p in model.parameters()):
+        import warnings
+        warnings.warn('bmcnet_esr_b200: eval()-mode forward with grad mode on runs the inference kernels and returns '
+                      'tensors without grad_fn; use .train() to record an autograd graph (or torch.no_grad() to '
+                      'silence this)')
+        _warned_eval_grad = True
+    return False
+
+
+def context(model):
+    tc = getattr(model, '_train_ctx', None)
+    if tc is None or tc.loss_scale != float(model.loss_scale):
+        tc = _Ctx(model.loss_scale)
+        model._train_ctx = tc
+    if len(tc.wcache) > 4096:            # stale versions of the weights (one set per optimiser step)
+        tc.wcache.clear()
+    return tc
+
+
+# ------------------------------------------------------------------------------------------ optimiser / collective
+def unique_parameters(model):
+    """The alias-deduplicated parameters (BMCNet: 2,731,680 elements; plain: 1,003,296)."""
+    return list(model.parameters())          # nn.Module.parameters() already yields each shared Parameter once
+
+
+class FusedAdamAMSGrad:
+    """torch.optim.Adam(lr, betas, eps, weight_decay, amsgrad=True) (config/train_nfs.yml:28-34) as ONE kernel over
+    flat fp32 buffers (bmc_adam_amsgrad_step).  The parameters are re-homed as views of one flat tensor."""
+
+    def __init__(self, params, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5):
+        self.params = [p for p in params]
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.step_count = 0
+        dev = self.params[0].device
+        if dev.type != 'cuda':
+            raise _lib.BmcError('FusedAdamAMSGrad needs CUDA parameters (no CPU fallback)')
+        n = sum(p.numel() for p in self.params)
+        self.flat = torch.empty(n, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(n, dtype=torch.float32, device=dev)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                k = p.numel()
+                self.flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = self.flat[off:off + k].view(p.shape)
+                p.grad = self.grad[off:off + k].view(p.shape)
+                off += k
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.vmax = torch.zeros_like(self.flat)
+
+    def zero_grad(self):
+        self.grad.zero_()
+        off = 0
+        for p in self.params:                     # `p.grad = None` by user code would detach the views: restore
+            k = p.numel()
+            if p.grad is None or p.grad.data_ptr() != self.grad.data_ptr() + off * 4:
+                p.grad = self.grad[off:off + k].view(p.shape)
+            off += k
+
+    def step(self):
+        self.step_count += 1
+        with torch.cuda.device(self.flat.device):
+            check(lib().bmc_adam_amsgrad_step(self.flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
+                                              self.vmax.data_ptr(), self.flat.numel(), self.step_count, self.lr,
+                                              self.betas[0], self.betas[1], self.eps, self.weight_decay, stream_ptr()))
+        for p in self.params:                     # the kernel wrote through raw pointers: make the change visible
+            torch.autograd.graph.increment_version(p)
+
+
+def allreduce_gradients(opt_or_params, group=None):
+    """Data-parallel gradient exchange: ONE all-reduce (NCCL over NVLink) of the alias-deduplicated
+    gradients, averaged over ranks.  With FusedAdamAMSGrad the gradients already live in one flat buffer."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if isinstance(opt_or_params, FusedAdamAMSGrad):
+        flat = opt_or_params.grad
+        dist.all_reduce(flat, group=group)
+        flat.div_(world)
+        return flat.numel()
+    grads = [p.grad for p in opt_or_params if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, group=group)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        g.copy_(flat[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return flat.numel()

@@ -278,6 +278,34 @@ int bmc_stack2cnt(const float* stack, int B, int TB, int H, int W, float* out, v
 int bmc_sr_metrics(const float* pred, int B, int C, int Hp, int Wp, const float* inp, int H, int W,
                    const float* gt, int Hg, int Wg, double* sums, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training step (reference train.py:202-237: forward over the sequence, summed nn.MSELoss, one backward,
+ * one optimiser step; config/train_nfs.yml:28-34: Adam(lr 1e-4, weight_decay 1e-5, amsgrad)).
+ * The autograd tape lives on the Python side (bmcnet_esr_b200/models/_train.py); these are its kernels.
+ *   data gradient (dgrad)   no entry of its own: it is bmc_conv_gemm on dY with the taps mirrored and the weight
+ *                           matrix transposed (what cuDNN's backward-data does for nn.Conv2d).
+ *   bmc_conv_wgrad          weight (and bias) gradient of `nn.Conv2d(k=3|1, padding=k/2)` w.r.t. ONE input source
+ *                           of a concatenated input: grad_w[co][cmap[ci]][tap] += scale * sum_rows dy[row][co] *
+ *                           x[row + off_tap][ci], grad_b[co] += scale * sum_rows dy[row][co] (grad_b may be NULL).
+ *                           dy: device act16 [B*R][128] with zero halo rows; x: device act16 [B*R][x_ch], x_ch = 64
+ *                           or 128; cmap: device int[x_ch], the input channel of the PyTorch-layout weight
+ *                           [n_out][cin_total][k][k] each source channel feeds, or -1 (padding); channels >= n_out of
+ *                           dy (a 32-output conv run as a zero-padded 128-output one) are ignored; grad_w / grad_b:
+ *                           device float, ACCUMULATED into (aliased modules share one gradient).
+ *                           tcgen05 split-K over n_split pixel ranges, partials reduced in a fixed order.
+ *   bmc_relu_backward       dx = dy * (y > 0) on act16 tensors (F.relu, BMCNet.py:64-73, submodules.py:33).
+ *   bmc_adam_amsgrad_step   torch.optim.Adam(amsgrad=True) with L2 weight decay over flat fp32 buffers; `step` is
+ *                           the 1-based step count.
+ * ---------------------------------------------------------------------------------------- */
+size_t bmc_conv_wgrad_workspace_bytes(int n_split, int taps, int x_ch);
+int bmc_conv_wgrad(const void* dy_act16, const void* x_act16, int x_ch, int taps, int B, int H, int W,
+                   const int* cmap, int cin_total, int n_out, float scale, float* grad_w, float* grad_b,
+                   void* workspace, size_t workspace_bytes, int n_split, void* stream);
+int bmc_relu_backward(const void* dy_act16, const void* y_act16, int64_t n_elems, void* dx_act16, void* stream);
+int bmc_adam_amsgrad_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                          float* max_exp_avg_sq, int64_t n, int step, float lr, float beta1, float beta2,
+                          float eps, float weight_decay, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
