@@ -369,6 +369,74 @@ def run_workload(cx, name, batch, Ksteps, Wsteps, sustained=True):
     return res
 
 
+def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
+    """BASELINE config 5: the BMCNet x4 training iteration of train.py:202-237 (8 recurrent steps with BPTT, summed
+    MSE, Adam(amsgrad); config/train_nfs.yml: batch 2, NFS LR 45x80), data-parallel: every rank runs its own
+    sequences through the kernels, ONE all-reduce averages the 2,731,680 alias-deduplicated gradients, fused Adam."""
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from bmcnet_esr_b200.models.BMCNet import BMCNet
+    from bmcnet_esr_b200.models._train import FusedAdamAMSGrad, allreduce_gradients
+    from oracle.make_golden import synth_counts
+    dev, world, rank = cx.dev, cx.world, cx.rank
+    sd, weights_desc = load_state('full')
+    model = BMCNet(4, 128, 5)
+    model.load_state_dict(sd, strict=True)
+    model = model.to(dev).train()
+    opt = FusedAdamAMSGrad(model.parameters())                  # lr 1e-4, wd 1e-5, amsgrad (train_nfs.yml:28-34)
+    xs = [synth_counts(batch, h, w, 3000 + 17 * rank + s).to(dev) for s in range(seq_steps)]
+    g = torch.Generator().manual_seed(5 + rank)
+    gts = [torch.poisson(torch.full((batch, 2, 4 * h, 4 * w), 0.3), generator=g).to(dev) for _ in range(seq_steps)]
+    n_red = 0
+
+    def iteration():
+        nonlocal n_red
+        opt.zero_grad()
+        st = [torch.zeros(batch, 128, h, w, device=dev) for _ in range(3)] + [torch.zeros(batch, 32, h, w, device=dev)]
+        loss, init = 0, True
+        for x, gt in zip(xs, gts):
+            st = list(model(x, *st, init))
+            init = False
+            loss = loss + F.mse_loss(st[-1], gt)
+        loss.backward()
+        if world > 1:
+            n_red = allreduce_gradients(opt)
+        opt.step()
+        return loss
+
+    for _ in range(warm):
+        iteration()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        loss = iteration()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / iters
+    finite = bool(torch.isfinite(loss))
+    del model, opt
+    torch.cuda.empty_cache()
+    return {'workload': 'BMCNet x4 training iteration (train.py:202-237): %d recurrent steps with BPTT, summed MSE, '
+                        'Adam(amsgrad), NFS LR %dx%d, batch %d per GPU, data-parallel' % (seq_steps, h, w, batch),
+            'weights': weights_desc, 'ms_per_iteration': ms, 'iterations_per_s': 1e3 / ms,
+            'value': batch * seq_steps * world / (ms * 1e-3), 'unit': 'training frames/s (forward + backward + update)',
+            'iterations': iters, 'batch_per_gpu': batch, 'sequence_steps': seq_steps, 'loss_finite': finite,
+            'allreduce': {'elements': n_red, 'bytes': n_red * 4, 'collective': 'one NCCL all-reduce of the flat '
+                          'alias-deduplicated fp32 gradient buffer per iteration'} if world > 1 else None,
+            'dtype': 'f16 activations / activation gradients under a static loss scale, fp32 weight gradients and Adam',
+            'kernels': 'every convolution forward / dgrad (bmc_conv_gemm) and wgrad (bmc_conv_wgrad) on tcgen05; LayerNorm, '
+                       '128x128 attention and layout glue are PyTorch ops'}
+
+
 def latency_b1(cx, model_kind, h, w, iters=60):
     """Batch-1 latency exactly as infer_BMCNet.py:54-68 measures it: a CUDA-event pair around the forward call of one
     recording's recurrent loop, synchronised every frame (so launch latency and the host side of `forward` count)."""
@@ -589,6 +657,7 @@ def main():
                 extra[name] = run_workload(cx, name, DEFAULT_BATCH[name], args.steps, args.warmup)
                 del cx.models[name]
                 torch.cuda.empty_cache()
+        extra['bmcnet_train_nfs'] = run_train(cx)
 
     if rank != 0:
         if world > 1:

@@ -113,3 +113,35 @@ def test_event_range_covers_once_and_stays_aligned():
             assert cuts[0][0] == 0 and cuts[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(cuts, cuts[1:]))
             assert all(lo <= hi and (lo % 4 == 0) for lo, hi in cuts)
+
+
+# ---- data-parallel training step: one all-reduce of the alias-deduplicated gradients ----
+def _grad_worker(rank, world, port, out):
+    from bmcnet_esr_b200.models.BMCNet import BMCNet
+    from bmcnet_esr_b200.models._train import allreduce_gradients, unique_parameters
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    m = BMCNet(4, 128, 5)
+    params = unique_parameters(m)
+    for i, p in enumerate(params):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = allreduce_gradients(params)
+    if rank == 0:
+        out.put((n, len(params), [p.grad.flatten()[0].item() for p in params[:3]], len(m.state_dict())))
+    dist.destroy_process_group()
+
+
+def test_gradient_allreduce_is_alias_deduplicated_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_grad_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    n, n_params, first, n_keys = q.get(timeout=300)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert n == 2731680 and n_params == 54 and n_keys == 318       # 318 keys, 54 Parameters, 2,731,680 elements
+    assert first == [1.5, 3.0, 4.5]                                # mean over the two ranks of (rank+1)*(i+1)
