@@ -19,7 +19,17 @@ constexpr int kSmemBudget = 227 * 1024;        // dynamic smem per CTA on sm_100
 constexpr int kMaxBinsSmem32 = 49152;          // 192 KB of int32 / fp32 bins
 constexpr int kMaxBinsSmem16 = kSmemBudget / 2;  // 16-bit packed bins
 
-enum Mode { kSmem32 = 0, kSmem16 = 1, kGlobal = 2 };
+enum Mode { kSmem32 = 0, kSmem16 = 1, kGlobal = 2, kSmem64 = 3, kGlobal64 = 4 };
+constexpr int kMaxBinsSmem64 = 24576;          // 192 KB of 64-bit fixed-point bins
+
+// BMC_ENC_DETERMINISTIC: float weights are accumulated as 64-bit fixed point (2^-32 units).  Integer addition is
+// associative, so the sum -- and the fp32 value it is rounded to once, in finalize64_kernel -- does not depend on
+// the order in which the atomics land: two runs are bit-identical, whatever the grid size or the scheduling.
+// |weight| < 2^30 per event and |sum| < 2^31 per bin; a weight's rounding error is <= 2^-33 (weights >= 2^-9 in
+// magnitude are represented exactly), far inside the 1e-6 bar.
+__device__ __forceinline__ unsigned long long to_fixed64(float w) {
+    return (unsigned long long)__double2ll_rn((double)w * 4294967296.0);
+}
 
 __device__ __forceinline__ float4 ldg_stream4(const float* p) {
     float4 v;
@@ -52,6 +62,8 @@ struct Hist {
     float* s_f;      // smem fp32 bins (FLOAT_HIST)
     int* g_cnt;      // global int32 grid
     float* g_ext;    // global fp32 grid (non-integral weights)
+    unsigned long long* s64;   // kSmem64: smem fixed-point bins
+    unsigned long long* g64;   // kSmem64 / kGlobal64: global fixed-point grid (overlays cnt + ext)
 
     __device__ __forceinline__ void add_int(int bin, int delta) {
         if (MODE == kSmem32) {
@@ -72,7 +84,9 @@ struct Hist {
         }
     }
     __device__ __forceinline__ void add_float(int bin, float w) {
-        if (FLOAT_HIST && MODE == kSmem32) atomicAdd(&s_f[bin], w);
+        if (MODE == kSmem64) atomicAdd(&s64[bin], to_fixed64(w));
+        else if (MODE == kGlobal64) atomicAdd(&g64[bin], to_fixed64(w));
+        else if (FLOAT_HIST && MODE == kSmem32) atomicAdd(&s_f[bin], w);
         else atomicAdd(&g_ext[bin], w);
     }
     // integral +-1 weights go to the exact integer path, everything else to fp32
@@ -270,7 +284,9 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nb
     h.s_f = reinterpret_cast<float*>(smem_raw);
     h.g_cnt = g_cnt;
     h.g_ext = g_ext;
-    const int words = (MODE == kSmem32) ? nbins : (MODE == kSmem16 ? (nbins + 1) / 2 : 0);
+    h.s64 = reinterpret_cast<unsigned long long*>(smem_raw);
+    h.g64 = reinterpret_cast<unsigned long long*>(g_cnt);
+    const int words = (MODE == kSmem32) ? nbins : (MODE == kSmem16 ? (nbins + 1) / 2 : (MODE == kSmem64 ? 2 * nbins : 0));
     for (int k = threadIdx.x; k < words; k += kThreads) h.s_i[k] = 0;
     if constexpr (Op::kBounds) {                 // bin ranges: 2*bins longs, read once per CTA
         __shared__ long s_bounds[128];
@@ -318,9 +334,14 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nb
         op.run(h, i, op.xs[i], op.ys[i], Op::kNeedT ? op.ts[i] : 0.f, op.ps[i]);
     }
 
-    if (MODE == kGlobal) return;
+    if (MODE == kGlobal || MODE == kGlobal64) return;
     __syncthreads();
-    if (MODE == kSmem32) {
+    if (MODE == kSmem64) {
+        for (int k = threadIdx.x; k < nbins; k += kThreads) {
+            const unsigned long long v = h.s64[k];
+            if (v) atomicAdd(&h.g64[k], v);
+        }
+    } else if (MODE == kSmem32) {
         for (int k = threadIdx.x; k < nbins; k += kThreads) {
             if (Op::kFloat) { const float v = h.s_f[k]; if (v != 0.f) atomicAdd(&g_ext[k], v); }
             else { const int v = h.s_i[k]; if (v != 0) atomicAdd(&g_cnt[k], v); }
@@ -514,6 +535,13 @@ __global__ void finalize_kernel(const int* __restrict__ cnt, const float* __rest
     out[i] = (float)c + ext[i];
 }
 
+// deterministic path: out = fp32(fixed-point sum * 2^-32), one rounding
+__global__ void finalize64_kernel(const long long* __restrict__ g64, float* __restrict__ out, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = (float)((double)g64[i] * (1.0 / 4294967296.0));
+}
+
 // Bin boundaries of the stack encoders, evaluated exactly like encodings.py:172-178 + :75-97
 // (float32, two roundings for ts[0] + delta_t*bi, any-equal binary search: every iteration tests ts[l], ts[r] and
 // ts[mid] for equality, in that order, before it halves the range).
@@ -696,7 +724,7 @@ int launch_threads(const Op& op, long n, int nbins, const Ws& w, int vec_ok, siz
     // n/g < nbins the flush term is n / 140e9 whatever g is, so small streams on large grids (n < 37 nbins) take
     // every SM; beyond that the minimum is at g = sqrt(36.8 n / nbins).
     long want = (n + (long)THREADS * 4 * 8 - 1) / ((long)THREADS * 4 * 8);
-    if (MODE != kGlobal) {
+    if (MODE != kGlobal && MODE != kGlobal64) {
         long by_flush = n / (4L * nbins) + 1;
         const double ratio = 36.8 * (double)n / (double)nbins;
         const long model = ratio < 36.8 * 37.0 ? (long)sm_count() * per_sm : (long)sqrt(ratio);
@@ -713,7 +741,7 @@ int launch_threads(const Op& op, long n, int nbins, const Ws& w, int vec_ok, siz
 
 template <class Op, int MODE>
 int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaStream_t st) {
-    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : 0);
+    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : (MODE == kSmem64 ? (size_t)nbins * 8 : 0));
     int per_sm = 1;
     BMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scatter_kernel<Op, MODE, kThreads>, kThreads, smem));
     // One 1024-thread CTA per SM keeps enough loads in flight (1024 x 2 groups x 3-4 arrays x 16 B >= 96 KB) and
@@ -721,7 +749,7 @@ int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaSt
     // grid was 4.3 M global atomics, 17 % of a 1e8-event launch.  Small streams keep the finer grid.
     static int fat = -1;
     if (fat < 0) fat = measure_env("BMC_ENC_FAT", 1);
-    if (per_sm < 2 || (fat && MODE != kGlobal && n >= (long)sm_count() * 1024 * 64))
+    if (per_sm < 2 || (fat && MODE != kGlobal && MODE != kGlobal64 && n >= (long)sm_count() * 1024 * 64))
         return launch_threads<Op, MODE, 1024>(op, n, nbins, w, vec_ok, smem, 1, st);
     return launch_threads<Op, MODE, kThreads>(op, n, nbins, w, vec_ok, smem, per_sm > 4 ? 4 : per_sm, st);
 }
@@ -737,6 +765,16 @@ int run_scatter(const Op& op, long n, long out_elems, float* out, void* ws, size
         const int vec_ok = (((uintptr_t)op.xs | (uintptr_t)op.ys | (uintptr_t)op.ps |
                              (uintptr_t)(Op::kNeedT ? op.ts : nullptr)) & 15) == 0;
         const int nbins = (int)out_elems;
+        if constexpr (Op::kFloat) {
+            if (op.flags & BMC_ENC_DETERMINISTIC) {
+                rc = out_elems <= kMaxBinsSmem64 ? launch_mode<Op, kSmem64>(op, n, nbins, w, vec_ok, st)
+                                                 : launch_mode<Op, kGlobal64>(op, n, nbins, w, vec_ok, st);
+                if (rc) return rc;
+                finalize64_kernel<<<(unsigned)((out_elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(w.cnt), out, out_elems);
+                BMC_CUDA(cudaGetLastError());
+                return BMC_OK;
+            }
+        }
         if (out_elems <= kMaxBinsSmem32) rc = launch_mode<Op, kSmem32>(op, n, nbins, w, vec_ok, st);
         else if (!Op::kFloat && !Op::kSigned && out_elems <= kMaxBinsSmem16)
             rc = launch_mode<Op, kSmem16>(op, n, nbins, w, vec_ok, st);
@@ -873,7 +911,7 @@ extern "C" BMC_EXPORT int bmc_encode_voxel(float* xs, float* ys, const float* ts
     op.xs = xs; op.ys = ys; op.ts = ts; op.ps = const_cast<float*>(ps);
     op.H = H; op.W = W; op.bins = bins; op.flags = flags;
     op.t0 = 0.f; op.dt = 1.f;     // BMC_ENC_TNORM: filled in on the device (VoxelOp::prepare)
-    if (bins >= 2 && (long)bins * H * W > kMaxBinsSmem32)      // too large for shared-memory bins
+    if (bins >= 2 && (long)bins * H * W > kMaxBinsSmem32 && !(flags & BMC_ENC_DETERMINISTIC))      // too large for shared-memory bins
         return run_voxel_pairs(op, n, out, workspace, workspace_bytes, as_stream(stream));
     return run_scatter(op, n, (long)bins * H * W, out, workspace, workspace_bytes, as_stream(stream));
 }

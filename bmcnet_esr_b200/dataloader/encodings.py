@@ -25,9 +25,37 @@ __all__ = ['interpolate_to_image', 'events_to_image_torch', 'binary_search_torch
            'events_to_voxel_torch', 'events_to_stack_polarity', 'events_to_stack_no_polarity',
            'events_to_image', 'events_to_voxel', 'events_to_channels', 'events_to_channels_windows',
            'python_event_redistribute_PolarityStack', 'python_event_redistribute_NoPolarityStack', 'stack2cnt',
-           'event_restore']
+           'event_restore', 'deterministic']
 
 _MUT = _lib.ENC_MUTATE
+
+# Bit-reproducible float encodings.  Count-valued encodings (events_to_channels, the stacks) are integer histograms
+# and always reproducible.  The float-weighted ones (events_to_voxel*, events_to_image* with non-unit weights) add
+# fp32 values with atomics, whose order changes from run to run (~1e-7 relative jitter).  With DETERMINISTIC = True
+# (or inside `with deterministic():`) they accumulate in 64-bit fixed point instead (BMC_ENC_DETERMINISTIC): the same
+# events give the same bits on every run, at roughly a third of the throughput.  The reference's function signatures
+# have no room for such a switch, hence the module-level one.
+DETERMINISTIC = False
+
+
+class deterministic:
+    """Context manager: `with deterministic(): events_to_voxel(...)`."""
+
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global DETERMINISTIC
+        self.prev, DETERMINISTIC = DETERMINISTIC, self.on
+        return self
+
+    def __exit__(self, *exc):
+        global DETERMINISTIC
+        DETERMINISTIC = self.prev
+
+
+def _det():
+    return _lib.ENC_DETERMINISTIC if DETERMINISTIC else 0
 
 
 def _chk(*ts):
@@ -62,7 +90,7 @@ def events_to_image(xs, ys, ps, sensor_size=(180, 240)):
     n = _chk(xs, ys, ps)
     h, w = sensor_size
     out = torch.empty(h, w, dtype=torch.float32, device=xs.device)
-    flags = _lib.ENC_FLIP_Y | _MUT
+    flags = _lib.ENC_FLIP_Y | _MUT | _det()
     return _run(lambda *a: lib().bmc_encode_image(_p(xs), _p(ys), _p(ps), n, h, w, *a, flags, stream_ptr()), out)
 
 
@@ -97,7 +125,7 @@ def events_to_voxel(xs, ys, ts, ps, num_bins, sensor_size=(180, 240)):
     n = _chk(xs, ys, ts, ps)
     h, w = sensor_size
     out = torch.empty(num_bins, h, w, dtype=torch.float32, device=xs.device)
-    flags = _lib.ENC_FLIP_Y | _MUT
+    flags = _lib.ENC_FLIP_Y | _MUT | _det()
     return _run(lambda *a: lib().bmc_encode_voxel(_p(xs), _p(ys), _p(ts), _p(ps), n, num_bins, h, w, *a, flags,
                                                   stream_ptr()), out)
 
@@ -117,7 +145,7 @@ def events_to_image_torch(xs, ys, ps, device=None, sensor_size=(180, 240), clip_
     (with padding) splats into a (H+1)x(W+1) image.  Mutates xs, ys, ps like the reference."""
     n = _chk(xs, ys, ps)
     h, w = sensor_size
-    flags = _MUT
+    flags = _MUT | _det()
     if interpolation == 'bilinear':
         if not padding:
             raise NotImplementedError('bilinear interpolation without padding (unused by the reference callers)')
@@ -222,7 +250,7 @@ def events_to_voxel_torch(xs, ys, ts, ps, B, device=None, sensor_size=(180, 240)
     assert len(xs) == len(ys) and len(ys) == len(ts) and len(ts) == len(ps)
     h, w = sensor_size
     out = torch.empty(B, h, w, dtype=torch.float32, device=xs.device)
-    flags = _lib.ENC_TNORM | _MUT
+    flags = _lib.ENC_TNORM | _MUT | _det()
     out = _run(lambda *a: lib().bmc_encode_voxel(_p(xs), _p(ys), _p(ts), _p(ps), n, B, h, w, *a, flags,
                                                  stream_ptr()), out)
     return out.to(device)

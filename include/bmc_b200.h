@@ -57,6 +57,9 @@ const char* bmc_act_dtype(void);
 #define BMC_ENC_TNORM 0x8u         /* voxel: t = (ts-ts[0])/dt*(B-1) (encodings.py:127-129) instead of ts*(B-1) (:280) */
 #define BMC_ENC_SKIP_ZERO_ENDS 0x20u /* stacks: ts[0]==0 && ts[n-1]==0 -> all-zero output, no event touched (see below) */
 #define BMC_ENC_BILINEAR 0x10u     /* image: spatial bilinear splat into (H+1)x(W+1) (encodings.py:57-65) */
+#define BMC_ENC_DETERMINISTIC 0x40u /* image / voxel: accumulate the float weights as 64-bit fixed point (2^-32 units) so the
+                                      result is bit-identical from run to run (integer sums do not depend on the order the
+                                      atomics land in); |weight| < 2^30 per event.  Count encodings are always deterministic. */
 
 /* Scratch bytes needed by any encoder call below for an output of `out_elems` floats. */
 size_t bmc_encode_workspace_bytes(int64_t out_elems);

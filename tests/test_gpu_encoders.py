@@ -241,3 +241,60 @@ def test_stack_one_bin_per_cta_kernel_unaligned_and_sharded(G):
             part = fn(cut[0], cut[1], ts_all, cut[2], lo, B, sensor_size=(h, w))
             acc = part if acc is None else acc + part
         assert np.array_equal(acc.cpu().numpy(), ref), name + ' sharded'
+
+
+@pytest.mark.parametrize('h,w,B,n', [(45, 80, 5, 3_000_017), (180, 320, 5, 2_000_003), (22, 40, 1, 70_001)])
+def test_deterministic_float_path_is_bit_reproducible_and_exact(G, h, w, B, n):
+    """BMC_ENC_DETERMINISTIC (`with deterministic():`): the float-weighted encodings accumulate in 64-bit fixed
+    point.  (1) two runs give identical bits -- also against a run on a shifted (unaligned -> scalar loads, another
+    grid) copy of the same events, i.e. a different summation order; (2) the value is the correctly rounded exact sum
+    up to 2^-33 per event: compared with a float64 accumulation of the SAME fp32 weights it agrees to 1 ulp of fp32;
+    (3) the default atomic path stays within the 1e-6 bar of it."""
+    ev = synth_events(n, h, w, seed=9, oor=0.0)
+
+    def run(det, shift=False):
+        a = _gpu(ev)
+        if shift:                                   # same values at a 4-byte offset: the kernel takes its scalar path
+            a = [torch.cat([t.new_zeros(1), t])[1:] for t in a]
+            assert a[0].data_ptr() % 16 != 0
+            a = [t for t in a]
+        with G.deterministic(det):
+            # views of a larger tensor are still contiguous 1-D float32
+            return G.events_to_voxel(a[0], a[1], a[2], a[3], B, sensor_size=(h, w)).cpu().numpy()
+
+    d1, d2, d3 = run(True), run(True), run(True, shift=True)
+    assert np.array_equal(d1, d2) and np.array_equal(d1, d3)
+    # float64 accumulation of the same fp32 weights (the oracle's weights, summed without fp32 rounding)
+    xs, ys, ts, ps = ev
+    tn = (ts * np.float32(B - 1)).astype(np.float32)
+    ref = np.zeros((B, h, w), np.float64)
+    yy = (h - 1 - np.trunc(ys).astype(np.int64))
+    xx = np.trunc(xs).astype(np.int64)
+    for b in range(B):
+        wgt = np.maximum(np.float32(0), np.float32(1) - np.abs(tn - np.float32(b))).astype(np.float32)
+        np.add.at(ref[b], (yy, xx), (ps * wgt).astype(np.float32).astype(np.float64))
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(d1 - ref).max() <= 2.0 ** -23 * scale, np.abs(d1 - ref).max()
+    nd = run(False)
+    assert np.abs(nd - d1).max() <= max(VOXEL_RTOL, 2.0 ** -24 * (n / (h * w)) * 4) * scale
+
+
+def test_deterministic_image_paths(G):
+    h, w, n = 45, 80, 400_003
+    ev = list(synth_events(n, h, w, seed=4, oor=0.01))
+    rng = np.random.default_rng(1)
+    ev[3] = (ev[3] * rng.random(n).astype(np.float32)).astype(np.float32)          # non-unit weights -> float path
+
+    def run(fn, **kw):
+        outs = []
+        for _ in range(2):
+            a = _gpu(ev)
+            with G.deterministic():
+                outs.append(fn(a[0], a[1], a[3], sensor_size=(h, w), **kw).cpu().numpy())
+        assert np.array_equal(outs[0], outs[1])
+        a = _gpu(ev)
+        base = fn(a[0], a[1], a[3], sensor_size=(h, w), **kw).cpu().numpy()
+        assert np.abs(base - outs[0]).max() <= 1e-5 * max(1.0, np.abs(base).max())
+    run(G.events_to_image)
+    run(G.events_to_image_torch)
+    run(G.events_to_image_torch, interpolation='bilinear')
