@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     __shared__ uint64_t in_full, in_empty, w_full[kFrontWStages], w_empty[kFrontWStages];
     __shared__ uint64_t acc_full[3], epi_done[2];      // per accumulator (A, B): strict ping-pong MMA <-> epilogue; [2] = U phase (both issuers)
     __shared__ uint32_t tmem_base_s;
-    __shared__ __align__(16) float bias_f[128], bias_c[128], bias_u[128], gam_s[128], bet_s[128];
+    __shared__ __align__(16) float bias_f[128], bias_c[128], bias_u[128];
     __shared__ float ln_sum[2][2][128], ln_var[2][2][128];     // [pass A / B][column half][row]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     if (threadIdx.x < 128) {
         const int t = threadIdx.x;
         bias_f[t] = p.bf[t]; bias_c[t] = p.bc[t]; bias_u[t] = p.bu[t];
-        gam_s[t] = p.ln_gamma[t]; bet_s[t] = p.ln_beta[t];
         const uint32_t one2 = pack_act2(1.f, 1.f);
         *reinterpret_cast<uint4*>(s_ones + t * 16) = make_uint4(one2, one2, one2, one2);
     }
@@ -188,10 +187,13 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             constexpr uint32_t half_units = kHalfBytes >> 4;
             int wi = 0, lt = 0;
             uint32_t epi_seen[2] = {0, 0};             // completions of epi_done[a] this thread has consumed or skipped
-            long long pw_in = 0, pw_w = 0, pw_epi = 0;
+            long long pw_in = 0, pw_w = 0, pw_epi = 0, pw_ws[3] = {0, 0, 0};
+            int w_site = 0;
             auto w_stage = [&](int j) -> uint32_t { return w_lo0 + ((wi + j) % kFrontWStages) * half_units; };
             auto wait_w = [&](int j) {
+                const long long _w0 = pw_w;
                 FPROF(pw_w, mbar_wait(&w_full[(wi + j) % kFrontWStages], ((wi + j) / kFrontWStages) & 1));
+                pw_ws[w_site] += pw_w - _w0;
                 tc_fence_after_sync();
             };
             auto free_w = [&](int j) { umma_commit(&w_empty[(wi + j) % kFrontWStages]); };
@@ -215,6 +217,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 if (lt > 0) wait_epi_n(0, eA - 1);              // U epilogue of the previous tile: A, B (s) and att are free
                 if (role == 0) {
                     // ---- Y1 -> A = [xs, x2] Wf^T
+                    w_site = 0;
                     for (int j = 0; j < 4; ++j) {
                         wait_w(j);
                         mma4(accA, (j < 2 ? xs_lo : x2_lo) + (j & 1) * half_units, w_stage(j), j > 0);
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     umma_commit(&acc_full[0]);
                     // ---- C1 -> A = yn1 Wc^T
                     wait_epi_n(0, eA);                          // LN(A): yn1 in s_y, A drained
+                    w_site = 1;
                     for (int j = 0; j < 2; ++j) {
                         wait_w(j);
                         mma4(accA, y_lo + j * half_units, w_stage(j), j > 0);
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     for (int s = 0; s < 8; ++s)                 // one K=16 slice = 16 pixel rows = 2048 B
                         umma_f16(att0, umma_desc(c_mn[0] + s * 128, hi), umma_desc(x_mn[0] + s * 128, hi), idesc_mn,
                                  (run_first && s == 0) ? 0u : 1u);
+                    w_site = 2;
                     for (int j = 0; j < 2; ++j) {
                         wait_w(j);
                         mma4(accA, y_lo + j * half_units, w_stage(j), j > 0);
@@ -269,6 +274,11 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     }
                     wi += 2;
                     umma_commit(&acc_full[1]);
+                    // this thread never reads Wu: its share of the four stages' release goes out now, so that the ring
+                    // frees up as soon as the OTHER thread's U MMAs retire and the producer can fetch the next
+                    // tile's Wf chunks before this tile ends (the MMA threads waited ~2.7 K cycles per tile on weights)
+                    for (int j = 0; j < 4; ++j) free_w(j);
+                    wi += 4;
                     // ---- att2 += c2^T x2 ; s_k = c_k^T 1 -> B[16k .. 16k+15]
                     wait_epi_n(1, eB + 1);                      // C(B): c2 in s_xs, B drained
 #pragma unroll
@@ -282,8 +292,6 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
 #pragma unroll
                     for (int s = 0; s < 8; ++s)
                         umma_f16(accB, umma_desc(c_mn[0] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
-                    for (int j = 0; j < 4; ++j) free_w(j);      // the Wu stages: this thread's share of the release
-                    wi += 4;
                 }
                 umma_commit(&in_empty);            // inputs and c tiles are consumed once both threads' MMAs retire
                 umma_commit(&acc_full[2]);         // U, s, att complete (both threads)
@@ -291,6 +299,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             if (prof_on && role == 0) {
                 long long* o = p.prof + blockIdx.x * 16;
                 o[0] = pw_in; o[1] = pw_w; o[2] = pw_epi; o[3] = clock64() - t_begin; o[4] = lt;
+                o[5] = pw_ws[0]; o[6] = pw_ws[1]; o[7] = pw_ws[2];
             }
             (void)epi_seen;
         }
@@ -304,6 +313,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
         const int tt = threadIdx.x - 96;           // 0..255
         uint32_t acc_uses[3] = {0, 0, 0};
         float s_run = 0.f;                         // running sum_px c_k[px, c] for k = ch, c = r
+        bool store_pending = false;                // this thread has an x_s' bulk store whose smem reads may be in flight
         int slot = segs_before(blockIdx.x, p.tiles_per_cta, tpi, p.lcm);
         long long pe_wait = 0, pe_ln = 0, pe_c = 0, pe_u = 0, pe_flush = 0;
         auto wait_acc = [&](int a) {
@@ -334,42 +344,39 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 tmem_ld_32x32(trow, v0);
                 tmem_ld_32x32(trow + 32, v1);
                 tmem_ld_wait();
-                float sum = 0.f;
+                // One pass over the 64 values of this thread: x = acc + bias, sum and sum of squares.  The two threads
+                // of a row (column halves, warps q and q + 4) exchange their partial moments once (a 64-thread named
+                // barrier per lane quarter).  var = E[x^2] - mu^2 in fp32 over 128 channels: the cancellation costs
+                // ~2^-24 * mu^2 / var relative, negligible against the fp16 rounding of the output.
+                // gamma and beta are NOT applied here: they are folded into the clustering weights / bias
+                // (model.cu, `clustering_ln`), so the normalisation is one FMA per element.
+                float sum = 0.f, sq = 0.f;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float x0 = __uint_as_float(v0[j]) + bias_f[ch * 64 + j];
                     const float x1 = __uint_as_float(v1[j]) + bias_f[ch * 64 + 32 + j];
                     v0[j] = __float_as_uint(x0); v1[j] = __float_as_uint(x1);
                     sum += x0 + x1;
-                }
-                // The two threads of a row (column halves, warps q and q + 4) merge their moments with ONE exchange:
-                // local mean / centred sum of squares over 64 channels each, then Chan's combination -- as accurate as
-                // the two global passes, one barrier fewer, and the barrier spans the two warps of a lane quarter only.
-                const float m_loc = sum * (1.f / 64.f);
-                float m2 = 0.f;
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float d0 = __uint_as_float(v0[j]) - m_loc, d1 = __uint_as_float(v1[j]) - m_loc;
-                    m2 += d0 * d0 + d1 * d1;
+                    sq = fmaf(x0, x0, sq);
+                    sq = fmaf(x1, x1, sq);
                 }
                 ln_sum[a][ch][r] = sum;
-                ln_var[a][ch][r] = m2;
+                ln_var[a][ch][r] = sq;
+                // (the quarter's store thread first makes sure the previous tile's bulk store has read its s_y rows)
+                if (a == 0 && store_pending) { tma_store_wait_read<0>(); store_pending = false; }
                 asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-                const float sum_o = ln_sum[a][ch ^ 1][r], m2_o = ln_var[a][ch ^ 1][r];
-                const float mu = (sum + sum_o) * (1.f / 128.f);
-                const float da = m_loc - mu, db = sum_o * (1.f / 64.f) - mu;
-                const float var = m2 + m2_o + 64.f * (da * da + db * db);
-                const float rstd = rsqrtf(var * (1.f / 128.f) + p.ln_eps);
+                const float mu = (sum + ln_sum[a][ch ^ 1][r]) * (1.f / 128.f);
+                const float var = fmaxf((sq + ln_var[a][ch ^ 1][r]) * (1.f / 128.f) - mu * mu, 0.f);
+                const float rstd = rsqrtf(var + p.ln_eps);
+                const float nb = -mu * rstd;
                 // (buffers alternate between the A and the B pass: the barrier of the next pass orders the reuse)
                 uint8_t* dst = a == 0 ? s_y : s_xs;
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    f[j] = gam_s[ch * 64 + j] * ((__uint_as_float(v0[j]) - mu) * rstd) + bet_s[ch * 64 + j];
+                for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v0[j]), rstd, nb);
                 store_tile_row32(dst, r, ch * 2, f);
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    f[j] = gam_s[ch * 64 + 32 + j] * ((__uint_as_float(v1[j]) - mu) * rstd) + bet_s[ch * 64 + 32 + j];
+                for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v1[j]), rstd, nb);
                 store_tile_row32(dst, r, ch * 2 + 1, f);
                 phase_done(a, true);
                 if (prof_on) pe_ln += clock64() - _tp;
@@ -395,23 +402,16 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 phase_done(a, true);
                 if (prof_on) pe_c += clock64() - _tp;
             }
-            // ---- U(A): x_s' = U + bu + x_s  (submodules.py:75); s_k from B
+            // ---- U(A): x_s' = x_s + (U + bu)  (submodules.py:75); s_k from B.
+            // The output overwrites x_s IN PLACE (the plan gives x_s' the slot of x_s): each lane quarter stages its
+            // [32 px x 128 ch] block of fp16(U + bu) in the (dead) c_1 tile in the TMA layout and one thread adds it
+            // onto the x_s rows in global memory with two bulk-tensor REDUCE-ADD stores -- no residual read, no
+            // per-thread global stores, no staged transposition (this pass was 3.3 K of ~18 K cycles per tile).
+            // x_s' = fp16(x_s + fp16(U + bu)): one more fp16 rounding of the 1x1 term than a single fp32 sum.
             {
                 const BieInst& in = p.inst[inst];
-                const long m_warp = (long)b * R + t * kTile + q * 32;      // first row of this warp's 32-row block
-                const act_t* res = p.act_base + ((long)in.xs_row + m_warp) * 128;
-                act_t* out = p.out_base + ((long)in.out_row + m_warp) * 128;
-                const int crow = lane >> 2, cchunk = lane & 3;             // coalesced mapping: row crow + 8i, 16-byte piece cchunk
-                // residual rows are fetched before the accumulator is awaited (latency off the critical path)
-                uint4 rv[2][4];
-#pragma unroll
-                for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        rv[cc][i] = *reinterpret_cast<const uint4*>(res + (long)(crow + 8 * i) * 128 + (ch * 2 + cc) * 32 + cchunk * 8);
                 wait_acc(2);
                 const long long _tp = prof_on ? clock64() : 0;
-                uint8_t* stage = s_y + e * 2048;                           // c_1 is dead: the MMAs that read it have retired
                 const uint32_t trow = tmem_base + lane_off + ch * 64;
                 uint32_t v0[32], v1[32], sv;
                 tmem_ld_32x32(trow, v0);
@@ -419,44 +419,22 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 tmem_ld_32x32_x1(tmem_base + 128 + lane_off + 16 * ch, sv);
                 tmem_ld_wait();
                 s_run += __uint_as_float(sv);
+                float f[32];
 #pragma unroll
-                for (int cc = 0; cc < 2; ++cc) {
-                    const int c = ch * 2 + cc;
-                    float f[32];
+                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v0[j]) + bias_u[ch * 64 + j] : 0.f;
+                store_tile_row32(s_y, r, ch * 2, f);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(cc == 0 ? v0[j] : v1[j]) + bias_u[c * 32 + j];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) *reinterpret_cast<uint4*>(stage + stage_off(crow + 8 * i, cchunk)) = rv[cc][i];
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const uint4 x = *reinterpret_cast<const uint4*>(stage + stage_off(lane, u));
-                        const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-                        for (int k2 = 0; k2 < 4; ++k2) {
-                            const float2 t2 = unpack_act2(w[k2]);
-                            f[u * 8 + k2 * 2] += t2.x;
-                            f[u * 8 + k2 * 2 + 1] += t2.y;
-                        }
-                    }
-                    __syncwarp();
-                    if (!valid) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = 0.f;
-                    }
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        *reinterpret_cast<uint4*>(stage + stage_off(lane, u)) =
-                            make_uint4(pack_act2(f[u * 8], f[u * 8 + 1]), pack_act2(f[u * 8 + 2], f[u * 8 + 3]),
-                                       pack_act2(f[u * 8 + 4], f[u * 8 + 5]), pack_act2(f[u * 8 + 6], f[u * 8 + 7]));
-                    __syncwarp();
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int row = crow + 8 * i;
-                        *reinterpret_cast<uint4*>(out + (long)row * 128 + c * 32 + cchunk * 8) =
-                            *reinterpret_cast<const uint4*>(stage + stage_off(row, cchunk));
-                    }
-                    __syncwarp();
+                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v1[j]) + bias_u[ch * 64 + 32 + j] : 0.f;
+                store_tile_row32(s_y, r, ch * 2 + 1, f);
+                fence_proxy_async_smem();
+                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+                if (ch == 0 && lane == 0) {
+                    const int grow = in.out_row + b * R + t * kTile + q * 32;
+                    tma_reduce_add_2d(&p.map_out, s_y + q * 4096, 0, grow);
+                    tma_reduce_add_2d(&p.map_out, s_y + kHalfBytes + q * 4096, 64, grow);
+                    tma_store_commit();
+                    store_pending = true;
+                    if (run_last) { tma_store_wait_read<0>(); store_pending = false; }     // the flush below reuses s_y
                 }
                 if (prof_on) pe_u += clock64() - _tp;
             }
@@ -494,6 +472,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             }
             phase_done(0, false);
         }
+        if (ch == 0 && lane == 0) tma_store_wait_all();           // the x_s' stores are complete before the kernel ends
         if (prof_on && tt == 0) {
             long long* o = p.prof + blockIdx.x * 16;
             o[8] = pe_wait; o[9] = pe_ln; o[10] = pe_c; o[11] = pe_u; o[12] = pe_flush; o[13] = clock64() - t_begin;
@@ -918,6 +897,7 @@ int launch_bie_front(const BieFrontParams& p, cudaStream_t st) {
         cudaMemcpy(h, prof, sizeof(h), cudaMemcpyDeviceToHost);
         for (int c : {0, 1, 73, 147}) {
             const long long* o = h + c * 16;
+            printf("frontprof cta %3d: wait_w by site: Wf %lld Wc %lld Wu %lld\n", c, o[5], o[6], o[7]);
             printf("frontprof cta %3d: tiles %lld | MMA wait_in %lld wait_w %lld wait_epi %lld of %lld | EPI wait_acc %lld ln %lld c %lld u %lld flush %lld of %lld\n",
                    c, o[4], o[0], o[1], o[2], o[3], o[8], o[9], o[10], o[11], o[12], o[13]);
         }

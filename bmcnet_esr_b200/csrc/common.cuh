@@ -199,6 +199,11 @@ __device__ __forceinline__ void tma_store_2d(const void* map, const void* smem_s
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
 }
+// 2-D tiled REDUCE shared -> global: global[box] += smem[box], element type from the tensor map (act16 add in L2)
+__device__ __forceinline__ void tma_reduce_add_2d(const void* map, const void* smem_src, int c0, int c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }

@@ -125,16 +125,17 @@ struct SoftmaxParams {
 // Fused 1x1 / attention section of BIE.forward (bie_fused.cu; submodules.py:63-75).
 constexpr int kMaxInst = 2;
 struct BieInst {
-    int x1_row, x2_row, xs_row, out_row;   // first arena row of x_1, x_2, x_s and of the x_s_ output
+    int x1_row, x2_row, xs_row, out_row;   // first arena row of x_1, x_2, x_s and of the x_s_ output (== xs_row: in place)
 };
 struct alignas(64) BieFrontParams {
     CUtensorMap map_act;                   // activation arena, box [128 rows][64 ch]
     CUtensorMap map_w;                     // static weights, box [128 rows][64]
+    CUtensorMap map_out;                   // activation arena, box [32 rows][64 ch]: the in-place x_s' reduce-add stores
     BieInst inst[kMaxInst];
     int n_inst;
-    int wf_row, wc_row, wu_row;            // first rows of convf (4 chunks), clustering (2), unclustering (4)
-    const float* bf; const float* bc; const float* bu;
-    const float* ln_gamma; const float* ln_beta; float ln_eps;
+    int wf_row, wc_row, wu_row;            // first rows of convf (4 chunks), clustering WITH norm_s's gamma folded in (2), unclustering (4)
+    const float* bf; const float* bc; const float* bu;     // bc: clustering bias + clustering weight . norm_s beta
+    float ln_eps;
     const act_t* act_base;                 // arena base (residual x_s rows / output rows)
     act_t* out_base;
     float* g_partial;                      // [slot][2][128][128]: sum_px c_k[px,c] * x_k[px,i]
@@ -205,6 +206,8 @@ int launch_emit(const EmitParams& p, cudaStream_t st);
 int launch_fill_identity(act_t* dst, cudaStream_t st);      // [2][128][64] chunk-major 128x128 identity
 int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out,
                          int n_out_pad, int K, act_t* dst, int w_rows, int w_row_base,
-                         cudaStream_t st);
+                         cudaStream_t st, const float* in_scale = nullptr);
+int launch_fold_beta_bias(const float* w, const float* bias, const float* beta, int n_out, int cin, float* bias_out,
+                          cudaStream_t st);
 
 }  // namespace bmc

@@ -96,6 +96,7 @@ struct SegSpec {
 };
 struct WeightSpec {
     std::string conv;        // state_dict prefix, e.g. "neuro.conv_f1"
+    std::string fold_ln;     // non-empty: prefix of the LayerNorm whose affine (gamma, beta) is folded into this 1x1 conv
     int cin, n_out, taps;
     std::vector<SegSpec> segs;
     int row_base = 0, k_chunks = 0;
@@ -237,6 +238,13 @@ void add_bie(bmc_model* m, const std::string& p) {
         add_weight(m, p + "." + n, p + "." + n, 256, 128, 1, {seg_range(0, 128, 128), seg_range(128, 128, 128)});
     for (const char* n : {"clustering", "v1", "v2"})
         add_weight(m, p + "." + n, p + "." + n, 128, 128, 1, {seg_range(0, 128, 128)});
+    // clustering(norm_s(y)) = (Wc diag(gamma)) n + (bc + Wc beta) with n = (y - mu) * rstd: the fused front kernel
+    // (bie_fused.cu) normalises without the affine part and multiplies by this folded copy
+    {
+        const int before = (int)m->weights.size();
+        const int wi = add_weight(m, p + ".clustering_ln", p + ".clustering", 128, 128, 1, {seg_range(0, 128, 128)});
+        if ((int)m->weights.size() > before) m->weights[wi].fold_ln = p + ".norm_s";
+    }
     if (m->widx.count(root_name(p + ".norm_s"))) return;
     LnSpec ln;
     ln.prefix = p + ".norm_s";
@@ -489,25 +497,24 @@ struct Builder {
             jobs.push_back(j);
         }
         gemm(jobs, 128, 9); jobs.clear();
-        for (int i = 0; i < I; ++i) ns[i] = alloc();
+        for (int i = 0; i < I; ++i) ns[i] = in[i].xs;           // x_s' is accumulated onto x_s in place (bie_front_tc)
         if (!m->dry) {
             const Geom& g = m->g;
             Op f;
             f.kind = Op::kBieFront;
             memset(&f.fp, 0, sizeof(f.fp));
             BieFrontParams& q = f.fp;
-            q.map_act = m->map_act; q.map_w = m->map_w128;
+            q.map_act = m->map_act; q.map_w = m->map_w128; q.map_out = m->map_act_out;
             q.n_inst = I;
             for (int i = 0; i < I; ++i) {
                 q.inst[i].x1_row = (int)(in[i].x1 * g.rows()); q.inst[i].x2_row = (int)(in[i].x2 * g.rows());
                 q.inst[i].xs_row = (int)(in[i].xs * g.rows()); q.inst[i].out_row = (int)(ns[i] * g.rows());
             }
-            const WeightSpec &wf = m->weights[W(p + ".convf1")], &wc = m->weights[W(p + ".clustering")],
+            const WeightSpec &wf = m->weights[W(p + ".convf1")], &wc = m->weights[W(p + ".clustering_ln")],
                              &wu = m->weights[W(p + ".unclustering")];
             q.wf_row = wf.row_base; q.wc_row = wc.row_base; q.wu_row = wu.row_base;
             q.bf = m->f32_dev + wf.bias_off; q.bc = m->f32_dev + wc.bias_off; q.bu = m->f32_dev + wu.bias_off;
-            const LnSpec& ln = m->lns[W(p + ".norm_s")];
-            q.ln_gamma = m->f32_dev + ln.gamma_off; q.ln_beta = m->f32_dev + ln.beta_off; q.ln_eps = 1e-6f;
+            q.ln_eps = 1e-6f;                                             // norm_s (submodules.py:48: LayerNorm2d default eps)
             q.act_base = m->slot_ptr(0); q.out_base = m->slot_ptr(0);
             q.g_partial = m->gpart_ptr(); q.s_partial = m->spart_ptr();
             q.g = g; q.tiles_per_img = g.R / 128;
@@ -541,7 +548,7 @@ struct Builder {
         std::vector<Tri> out(I);
         for (int i = 0; i < I; ++i) {
             for (int k = 0; k < 2; ++k) release(t[i][k]);
-            release(in[i].x1); release(in[i].x2); release(in[i].xs);
+            release(in[i].x1); release(in[i].x2);               // (the x_s slot lives on as x_s')
             out[i] = {nx[i][0], nx[i][1], ns[i]};
         }
         return out;
@@ -812,10 +819,22 @@ extern "C" BMC_EXPORT int bmc_model_load_state_dict(bmc_model_t* m, const char* 
         rc = find(w.conv + ".bias", w.n_out, &bs);
         if (rc) return rc;
         // weight w occupies rows [row_base, row_base + k_chunks * n_out): chunk-major [k_chunks][n_out][64]
+        const float *gam = nullptr, *bet = nullptr;
+        if (!w.fold_ln.empty()) {
+            rc = find(w.fold_ln + ".weight", w.cin, &gam);
+            if (rc) return rc;
+            rc = find(w.fold_ln + ".bias", w.cin, &bet);
+            if (rc) return rc;
+        }
         rc = launch_repack_weight(wt, m->kmap_dev + koffs[i], w.cin * w.taps, w.n_out, w.n_out, w.k_chunks * 64,
-                                  m->w_dev + (size_t)w.row_base * 64, w.n_out, 0, st);
+                                  m->w_dev + (size_t)w.row_base * 64, w.n_out, 0, st, gam);
         if (rc) return rc;
-        BMC_CUDA(cudaMemcpyAsync(m->f32_dev + w.bias_off, bs, w.n_out * 4, cudaMemcpyDeviceToDevice, st));
+        if (bet) {
+            rc = launch_fold_beta_bias(wt, bs, bet, w.n_out, w.cin, m->f32_dev + w.bias_off, st);
+            if (rc) return rc;
+        } else {
+            BMC_CUDA(cudaMemcpyAsync(m->f32_dev + w.bias_off, bs, w.n_out * 4, cudaMemcpyDeviceToDevice, st));
+        }
     }
     {
         int rc = launch_fill_identity(m->w_dev + (size_t)m->ident_row * 64, st);

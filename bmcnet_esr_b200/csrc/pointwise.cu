@@ -231,15 +231,28 @@ __global__ void __launch_bounds__(128) emit_output(EmitParams p) {
 // fp32 conv weight [n_out][*] -> bf16 chunk-major [K/64][w_rows][64] at rows
 // [w_row_base, w_row_base + n_out_pad); kmap[k] = flat offset inside one output-channel row of
 // the source, or -1 for zero padding.
+// `in_scale` (optional, 1x1 weights only: source offset == input channel): the weight of input channel i is
+// multiplied by in_scale[i] -- a channel LayerNorm's gamma folded into the convolution that follows it.
 __global__ void repack_weight(const float* __restrict__ src, const int* __restrict__ kmap, int src_row_len,
                               int n_out, int n_out_pad, int K, act_t* __restrict__ dst, int w_rows,
-                              int w_row_base) {
+                              int w_row_base, const float* __restrict__ in_scale) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)n_out_pad * K) return;
     const int n = (int)(idx / K), k = (int)(idx - (long)n * K);
     const int off = kmap[k];
-    const float v = (n < n_out && off >= 0) ? src[(long)n * src_row_len + off] : 0.f;
+    float v = (n < n_out && off >= 0) ? src[(long)n * src_row_len + off] : 0.f;
+    if (in_scale && off >= 0) v *= in_scale[off];
     dst[((long)(k >> 6) * w_rows + w_row_base + n) * 64 + (k & 63)] = to_act(v);
+}
+
+// bias_out[o] = bias[o] + sum_i w[o][i] * beta[i]: the LayerNorm's beta pushed through a 1x1 convolution (fp32)
+__global__ void fold_beta_bias(const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ beta,
+                               int n_out, int cin, float* __restrict__ bias_out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= n_out) return;
+    float s = bias[o];
+    for (int i = 0; i < cin; ++i) s += w[(long)o * cin + i] * beta[i];
+    bias_out[o] = s;
 }
 
 __global__ void fill_identity(act_t* __restrict__ dst) {
@@ -301,10 +314,17 @@ int launch_emit(const EmitParams& p, cudaStream_t st) {
 }
 
 int launch_repack_weight(const float* src, const int* kmap, int src_row_len, int n_out, int n_out_pad, int K,
-                            act_t* dst, int w_rows, int w_row_base, cudaStream_t st) {
+                            act_t* dst, int w_rows, int w_row_base, cudaStream_t st, const float* in_scale) {
     const long total = (long)n_out_pad * K;
     repack_weight<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, kmap, src_row_len, n_out, n_out_pad, K, dst,
-                                                                  w_rows, w_row_base);
+                                                                  w_rows, w_row_base, in_scale);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+int launch_fold_beta_bias(const float* w, const float* bias, const float* beta, int n_out, int cin, float* bias_out,
+                          cudaStream_t st) {
+    fold_beta_bias<<<(n_out + 127) / 128, 128, 0, st>>>(w, bias, beta, n_out, cin, bias_out);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }
