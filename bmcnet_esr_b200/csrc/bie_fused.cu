@@ -22,15 +22,20 @@
 //   warps 3-10  epilogue: all eight work on ONE accumulator at a time (lane quarter x column half)
 // Two accumulators A and B ping-pong so the tensor core works on one k-path while the epilogue
 // warps post-process the other:
-//   MMA       Y1->A   Y2->B   C1->A      C2->B      att1,U(c1)->A    att2,s1,s2->B,U(c2)->A
-//   epilogue          LN(A)   LN(B)      C(A)       C(B)                               U(A)+s(B) [+flush]
-//   Y_k = [x_s, x_other] Wf^T ; LN = +bias, channel LayerNorm -> fp16 tile yn_k in smem (A operand of C_k)
-//   C_k = yn_k Wc^T ; C() = +bias, halo rows -> 0 -> fp16 tile c_k in smem
+//   MMA       Y1->A   Y2->B   C1->A      C2->B      att1,s1->A[0:16]   att2, s2->A[16:32], U->B     | Y1'->A (next tile)
+//   epilogue          LN(A)   LN(B)      C(A)       C(B)                                  s(A) U(B) [+flush]
+//   Y_k = [x_s, x_other] Wf^T ; LN = +bias, channel normalisation (x - mu) * rstd -> fp16 tile yn_k in smem (A operand
+//         of C_k); norm_s's gamma / beta are folded into the clustering weights / bias on the host (model.cu)
+//   C_k = yn_k Wc'^T ; C() = +bias', halo rows -> 0 -> fp16 tile c_k in smem
 //   att_k += c_k^T x_k (pixel-major operands, persistent TMEM accumulators over a run of tiles of one image)
 //   s_k = c_k^T 1 (an N=16 MMA against a block of ones: column 0 of row c is sum_px c_k[px, c])
-//   U = [c_1, c_2] Wu^T ; U() = +bias + x_s -> x_s' to HBM
-// Buffers: yn_1/c_1 own a tile; yn_2/c_2 overwrite the x_s tile (dead once Y2's MMAs retire).
+//   U = [c_1, c_2] Wu^T ; U() = fp16(U + bias), added onto the x_s rows IN PLACE by TMA reduce-add stores
+// U sits in B and s in A, and the U pass reads s first: A goes back to the MMA thread a few hundred cycles into the
+// last epilogue pass, so the next tile's input loads and Y1 MMAs overlap it.
+// Buffers: yn_1/c_1 own a tile (then the store staging); yn_2/c_2 overwrite the x_s tile (dead once Y2's MMAs retire).
 // TMEM: A, B (2 x 128 columns) + att_1, att_2 (2 x 128 columns) = 512.
+// Measured per launch at B = 95 (plain, 45x80): 226 us (round 1) -> 210 (reduce-add U pass) -> 194 (one-pass
+// moments, folded affine) -> see DESIGN.md for the current figure.
 #include "gemm_epi.cuh"
 
 namespace bmc {
@@ -86,7 +91,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     uint8_t* s_ones = s_w + kFrontWStages * kHalfBytes;
 
     __shared__ uint64_t in_full, in_empty, w_full[kFrontWStages], w_empty[kFrontWStages];
-    __shared__ uint64_t acc_full[3], epi_done[2];      // per accumulator (A, B): strict ping-pong MMA <-> epilogue; [2] = U phase (both issuers)
+    __shared__ uint64_t acc_full[3];                   // MMA -> epilogue: accumulator A / B complete (twice per tile each); [2] = U, s, att (both issuers)
+    __shared__ uint64_t ln_done[2], c_done[2], a_free, u_done;     // epilogue -> MMA, once per tile each (see the issuers)
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_f[128], bias_c[128], bias_u[128];
     __shared__ float ln_sum[2][2][128], ln_var[2][2][128];     // [pass A / B][column half][row]
@@ -101,8 +107,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     if (threadIdx.x == 0) {
         mbar_init(&in_full, 1); mbar_init(&in_empty, 2);
         for (int s = 0; s < kFrontWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&epi_done[s], 8); }
-        mbar_init(&acc_full[2], 2);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&ln_done[s], 8); mbar_init(&c_done[s], 8); }
+        mbar_init(&acc_full[2], 2); mbar_init(&a_free, 8); mbar_init(&u_done, 8);
         mbar_fence_init();
         tma_prefetch_desc(&p.map_act);
         tma_prefetch_desc(&p.map_w);
@@ -186,7 +192,6 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             const uint32_t w_lo0 = umma_desc_lo(smem_u32(s_w), 16);
             constexpr uint32_t half_units = kHalfBytes >> 4;
             int wi = 0, lt = 0;
-            uint32_t epi_seen[2] = {0, 0};             // completions of epi_done[a] this thread has consumed or skipped
             long long pw_in = 0, pw_w = 0, pw_epi = 0, pw_ws[3] = {0, 0, 0};
             int w_site = 0;
             auto w_stage = [&](int j) -> uint32_t { return w_lo0 + ((wi + j) % kFrontWStages) * half_units; };
@@ -197,25 +202,30 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 tc_fence_after_sync();
             };
             auto free_w = [&](int j) { umma_commit(&w_empty[(wi + j) % kFrontWStages]); };
-            // wait for the n-th completion (0-based, counted from kernel start) of epi_done[a]
-            auto wait_epi_n = [&](int a, uint32_t n) {
-                FPROF(pw_epi, mbar_wait(&epi_done[a], n & 1));
-                tc_fence_after_sync();
-            };
             auto mma4 = [&](uint32_t acc, uint32_t a_lo, uint32_t b_lo, uint32_t first_acc) {
                 umma_f16(acc, umma_desc(a_lo, hi), umma_desc(b_lo, hi), idesc_k, first_acc);
                 umma_f16(acc, umma_desc(a_lo + 2, hi), umma_desc(b_lo + 2, hi), idesc_k, 1u);
                 umma_f16(acc, umma_desc(a_lo + 4, hi), umma_desc(b_lo + 4, hi), idesc_k, 1u);
                 umma_f16(acc, umma_desc(a_lo + 6, hi), umma_desc(b_lo + 6, hi), idesc_k, 1u);
             };
-            // epi_done[0] completes 3x per tile (LN(A), C(A), U), epi_done[1] 2x (LN(B), C(B))
+            // Epilogue -> MMA events, one mbarrier each, every one completing exactly once per tile (parity = tile
+            // parity; a thread only ever waits on barriers whose every phase it observes, see gemm_slab2.cu):
+            //   ln_done[a]  yn_a is in shared memory, accumulator a drained      c_done[a]  likewise for c_a
+            //   a_free      the U pass has read s_1, s_2 out of A: the next tile's Y1 may overwrite A
+            //   u_done      end of the tile's epilogue: B (U) is drained
+            // U accumulates into B and s into A[0:32]: A is handed back a few hundred cycles into the U pass, so the
+            // next tile's Y1 MMAs (and its input loads, released by the commit below) overlap this tile's U epilogue.
             for (int T = T0; T < T1; ++T, ++lt) {
                 const bool run_first = lt == 0 || (T % tpi) == 0;
-                const uint32_t eA = 3u * lt, eB = 2u * lt;      // completions before this tile
+                const uint32_t par = lt & 1, ppar = (lt - 1) & 1;
+                auto wait_bar = [&](uint64_t* bar, uint32_t parity) {
+                    FPROF(pw_epi, mbar_wait(bar, parity));
+                    tc_fence_after_sync();
+                };
                 FPROF(pw_in, mbar_wait(&in_full, lt & 1));
                 tc_fence_after_sync();
-                if (lt > 0) wait_epi_n(0, eA - 1);              // U epilogue of the previous tile: A, B (s) and att are free
                 if (role == 0) {
+                    if (lt > 0) wait_bar(&a_free, ppar);        // s of the previous tile has been read out of A
                     // ---- Y1 -> A = [xs, x2] Wf^T
                     w_site = 0;
                     for (int j = 0; j < 4; ++j) {
@@ -226,7 +236,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     wi += 4;
                     umma_commit(&acc_full[0]);
                     // ---- C1 -> A = yn1 Wc^T
-                    wait_epi_n(0, eA);                          // LN(A): yn1 in s_y, A drained
+                    wait_bar(&ln_done[0], par);                 // yn1 in s_y, A drained
                     w_site = 1;
                     for (int j = 0; j < 2; ++j) {
                         wait_w(j);
@@ -235,29 +245,30 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     }
                     wi += 2;
                     umma_commit(&acc_full[0]);
-                    // ---- att1 += c1^T x1 ; U -> A = c1 Wu[0..1]^T
-                    wait_epi_n(0, eA + 1);                      // C(A): c1 in s_y, A drained
+                    // ---- att1 += c1^T x1 ; s_1 = c1^T 1 -> A[0..15]
+                    wait_bar(&c_done[0], par);                  // c1 in s_y, A drained
 #pragma unroll
                     for (int s = 0; s < 8; ++s)                 // one K=16 slice = 16 pixel rows = 2048 B
                         umma_f16(att0, umma_desc(c_mn[0] + s * 128, hi), umma_desc(x_mn[0] + s * 128, hi), idesc_mn,
                                  (run_first && s == 0) ? 0u : 1u);
-                    w_site = 2;
-                    for (int j = 0; j < 2; ++j) {
-                        wait_w(j);
-                        mma4(accA, y_lo + j * half_units, w_stage(j), j > 0);
-                        free_w(j);
-                    }
-                    wi += 2;
-                    // ---- U += c2 Wu[2..3]^T
-                    wait_epi_n(1, eB + 1);                      // C(B): c2 in s_xs
-                    for (int j = 0; j < 2; ++j) {
-                        wait_w(j);
-                        mma4(accA, xs_lo + j * half_units, w_stage(j), 1u);
-                        free_w(j);
-                    }
-                    wi += 2;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        umma_f16(accA, umma_desc(c_mn[0] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
+                    // ---- s_2 = c2^T 1 -> A[16..31]
+                    wait_bar(&c_done[1], par);                  // c2 in s_xs
+                    // This thread never reads Wu: its share of the four stages' release.  Not earlier than this point:
+                    // an mbarrier cannot tell WHOSE arrivals it counts, so this thread must not arrive for a stage's
+                    // Wu use before the other thread has arrived for the stage's previous use (Wf1..3, Wc0) -- which it
+                    // has once C(B) is done (its release of Wc precedes the commit that C(B) waited for).
+                    for (int j = 0; j < 4; ++j) free_w(j);
+                    wi += 4;
+#pragma unroll
+                    for (int s = 0; s < 8; ++s)
+                        umma_f16(accA + 16, umma_desc(c_mn[1] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
                 } else {
+                    if (lt > 0) wait_bar(&u_done, ppar);        // U of the previous tile has been read out of B
                     // ---- Y2 -> B = [xs, x1] Wf^T
+                    w_site = 0;
                     for (int j = 0; j < 4; ++j) {
                         wait_w(j);
                         mma4(accB, (j < 2 ? xs_lo : x1_lo) + (j & 1) * half_units, w_stage(j), j > 0);
@@ -266,7 +277,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     wi += 4;
                     umma_commit(&acc_full[1]);
                     // ---- C2 -> B = yn2 Wc^T
-                    wait_epi_n(1, eB);                          // LN(B): yn2 in s_xs, B drained
+                    wait_bar(&ln_done[1], par);                 // yn2 in s_xs, B drained
+                    w_site = 1;
                     for (int j = 0; j < 2; ++j) {
                         wait_w(j);
                         mma4(accB, xs_lo + j * half_units, w_stage(j), j > 0);
@@ -274,24 +286,19 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     }
                     wi += 2;
                     umma_commit(&acc_full[1]);
-                    // this thread never reads Wu: its share of the four stages' release goes out now, so that the ring
-                    // frees up as soon as the OTHER thread's U MMAs retire and the producer can fetch the next
-                    // tile's Wf chunks before this tile ends (the MMA threads waited ~2.7 K cycles per tile on weights)
-                    for (int j = 0; j < 4; ++j) free_w(j);
-                    wi += 4;
-                    // ---- att2 += c2^T x2 ; s_k = c_k^T 1 -> B[16k .. 16k+15]
-                    wait_epi_n(1, eB + 1);                      // C(B): c2 in s_xs, B drained
+                    // ---- att2 += c2^T x2 ; U -> B = c1 Wu[0..1]^T + c2 Wu[2..3]^T
+                    wait_bar(&c_done[1], par);                  // c2 in s_xs (and c1 in s_y: C(A) precedes C(B)), B drained
 #pragma unroll
                     for (int s = 0; s < 8; ++s)
                         umma_f16(att0 + 128, umma_desc(c_mn[1] + s * 128, hi), umma_desc(x_mn[1] + s * 128, hi), idesc_mn,
                                  (run_first && s == 0) ? 0u : 1u);
-#pragma unroll
-                    for (int s = 0; s < 8; ++s)
-                        umma_f16(accB + 16, umma_desc(c_mn[1] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
-                    wait_epi_n(0, eA + 1);                      // C(A): c1 in s_y
-#pragma unroll
-                    for (int s = 0; s < 8; ++s)
-                        umma_f16(accB, umma_desc(c_mn[0] + s * 128, hi), umma_desc(ones_mn, hi), idesc_s, s == 0 ? 0u : 1u);
+                    w_site = 2;
+                    for (int j = 0; j < 4; ++j) {
+                        wait_w(j);
+                        mma4(accB, (j < 2 ? y_lo : xs_lo) + (j & 1) * half_units, w_stage(j), j > 0);
+                        free_w(j);
+                    }
+                    wi += 4;
                 }
                 umma_commit(&in_empty);            // inputs and c tiles are consumed once both threads' MMAs retire
                 umma_commit(&acc_full[2]);         // U, s, att complete (both threads)
@@ -301,7 +308,6 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 o[0] = pw_in; o[1] = pw_w; o[2] = pw_epi; o[3] = clock64() - t_begin; o[4] = lt;
                 o[5] = pw_ws[0]; o[6] = pw_ws[1]; o[7] = pw_ws[2];
             }
-            (void)epi_seen;
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 3..10)
@@ -321,11 +327,11 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             ++acc_uses[a];
             tc_fence_after_sync();
         };
-        auto phase_done = [&](int a, bool wrote_smem) {
+        auto phase_done = [&](uint64_t* bar, bool wrote_smem) {
             if (wrote_smem) fence_proxy_async_smem();
             tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&epi_done[a]);
+            if (lane == 0) mbar_arrive(bar);
         };
         for (int T = T0; T < T1; ++T) {
             const int img = T / tpi, t = T - img * tpi;
@@ -378,7 +384,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v1[j]), rstd, nb);
                 store_tile_row32(dst, r, ch * 2 + 1, f);
-                phase_done(a, true);
+                phase_done(&ln_done[a], true);
                 if (prof_on) pe_ln += clock64() - _tp;
             }
             // ---- C(A), C(B): c_k = C_k + bc, halo rows zero  (`clustering`, submodules.py:63-64)
@@ -399,7 +405,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v1[j]) + bias_c[ch * 64 + 32 + j] : 0.f;
                 store_tile_row32(dst, r, ch * 2 + 1, f);
-                phase_done(a, true);
+                phase_done(&c_done[a], true);
                 if (prof_on) pe_c += clock64() - _tp;
             }
             // ---- U(A): x_s' = x_s + (U + bu)  (submodules.py:75); s_k from B.
@@ -412,13 +418,15 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 const BieInst& in = p.inst[inst];
                 wait_acc(2);
                 const long long _tp = prof_on ? clock64() : 0;
-                const uint32_t trow = tmem_base + lane_off + ch * 64;
                 uint32_t v0[32], v1[32], sv;
+                tmem_ld_32x32_x1(tmem_base + lane_off + 16 * ch, sv);         // s_k: column 0 of A[16 k .. 16 k + 15]
+                tmem_ld_wait();
+                phase_done(&a_free, false);                                   // A may take the next tile's Y1 now
+                s_run += __uint_as_float(sv);
+                const uint32_t trow = tmem_base + 128 + lane_off + ch * 64;   // U lives in B
                 tmem_ld_32x32(trow, v0);
                 tmem_ld_32x32(trow + 32, v1);
-                tmem_ld_32x32_x1(tmem_base + 128 + lane_off + 16 * ch, sv);
                 tmem_ld_wait();
-                s_run += __uint_as_float(sv);
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v0[j]) + bias_u[ch * 64 + j] : 0.f;
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 ++slot;
                 if (prof_on) pe_flush += clock64() - _tp;
             }
-            phase_done(0, false);
+            phase_done(&u_done, false);
         }
         if (ch == 0 && lane == 0) tma_store_wait_all();           // the x_s' stores are complete before the kernel ends
         if (prof_on && tt == 0) {
