@@ -9,7 +9,11 @@ Differences a caller can observe:
   * count-valued encodings are bit-exact; float-weighted ones (events_to_voxel*, weighted
     events_to_image*) accumulate in a different order than the reference's serial loop and agree
     to ~1e-6 relative;
-  * NaN coordinates are dropped (the reference indexes with garbage).
+  * NaN coordinates are dropped (the reference indexes with garbage);
+  * `event_restore` and `stack2cnt` return tensors on the caller's CUDA device; the reference moves its argument
+    to the host first (`.cpu()`, encodings.py:594,658) and returns CPU tensors -- append `.cpu()` for that;
+  * the reference's `ts.sum() == 0` early-out of the stack / voxel_torch encoders is decided from the two end
+    stamps first and a full scan only when both are zero (exact for any input, one 4-byte read-back per call).
 Reproduced on purpose (bit-exact parity): out-of-range events are zeroed in the
 caller's xs / ys (/ ps), the leak of such events into pixel (0,0) on later passes, and the double
 counting of bin-boundary events by the any-equal binary search.
@@ -71,10 +75,26 @@ def _chk(*ts):
     return n
 
 
+_WS = {}       # (device index, stream) -> scratch tensor, grown on demand
+
+
+def _workspace(dev, nbytes):
+    """Scratch for one encoder call.  The library clears what it uses at the start of every call (on the call's
+    stream), so one buffer per (device, stream) is reused instead of a fresh `torch.empty` per call; calls on the
+    same stream are ordered, calls on different streams get different buffers."""
+    with torch.cuda.device(dev):
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _WS[key] = ws
+    return ws
+
+
 def _run(fn, out, *args):
     """Call an encoder entry with a scratch workspace sized for `out`."""
     nbytes = lib().bmc_encode_workspace_bytes(out.numel())
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=out.device)
+    ws = _workspace(out.device, nbytes)
     with torch.cuda.device(out.device):
         check(fn(*args, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes))
     return out
@@ -203,7 +223,7 @@ def _stack_call(xs, ys, ps, ts_all, first, B, sensor_size, polarity):
         return torch.zeros([B, h, w], device=xs.device)
     out = torch.empty(*((2, B, h, w) if polarity else (B, h, w)), dtype=torch.float32, device=xs.device)
     nbytes = lib().bmc_encode_workspace_bytes(out.numel())
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=out.device)
+    ws = _workspace(out.device, nbytes)
 
     def launch(flags):
         with torch.cuda.device(out.device):

@@ -69,6 +69,33 @@ class BMCNet(nn.Module):
             (h, hp, hn), o = self._engine.forward(self, x, [x_h, x_h_p, x_h_n], x_o, init)
         return h, hp, hn, o
 
+    # -- weights / state tracking (models/_engine.py): edits the engine cannot see by itself
+    def refresh_weights(self):
+        """Re-pack the weights (and forget the resident recurrent state) on the next call.  Needed only after writes
+        that bypass the Parameters' version counters, i.e. through `param.data` (`p.data.mul_()`, `p.data.copy_()`,
+        EMA / clamp code); `load_state_dict`, `.to()`, optimiser steps and in-place ops on the Parameters are
+        detected automatically."""
+        self._engine.invalidate()
+
+    @property
+    def resident_state_fast_path(self):
+        return self._engine.fast_path
+
+    @resident_state_fast_path.setter
+    def resident_state_fast_path(self, on):
+        self._engine.fast_path = bool(on)
+        self._engine._last = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._engine.invalidate()
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._engine.invalidate()
+        return out
+
     def step(self, x, reset=False, want_output=True):
         with torch.no_grad():
             return self._engine.step(self, x, reset, want_output)

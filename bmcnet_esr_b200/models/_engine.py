@@ -1,11 +1,19 @@
 """Host glue between the nn.Module mirrors and the C-ABI model object (bmc_model_*).
 
 One Engine per module instance.  It owns (as torch tensors, so the caching allocator stays in
-charge) the repacked bf16 weight buffer and the activation arena, and re-creates them when the
+charge) the repacked 16-bit weight buffer and the activation arena, and re-creates them when the
 parameters, the device or the problem size change:
   * parameters are re-packed whenever any Parameter's (data_ptr, _version) changed -- i.e. after
-    load_state_dict, .to(device) or an optimiser step;
+    load_state_dict, .to(device), an optimiser step or any in-place op on the Parameter itself -- and whenever
+    the owning module calls `invalidate()` (it does after `load_state_dict` and every `_apply`: `.to`, `.cuda`,
+    `.float`, ...).
+    NOT detected: writes through `param.data` (`p.data.mul_(2)`, `p.data.copy_(...)`, EMA / clamp code): `.data`
+    does not share the Parameter's version counter.  After such an edit call `model.refresh_weights()`.
   * the arena / plan are rebuilt when (B, H, W) changes.
+The same caveat holds for the resident-state fast path of `forward` (the recurrent state is not re-packed when the
+call is handed back the previous call's own, untouched output tensors): an edit of those tensors through `.data` is
+not seen; set `model.resident_state_fast_path = False` (or call `model.refresh_weights()`, which also forgets the
+resident state) if a caller does that.
 """
 import ctypes as C
 
@@ -26,6 +34,12 @@ class Engine:
         self.param_sig = None
         self.debug_simt = False
         self._last = None          # the tensors returned by the previous forward() (and their versions)
+        self.fast_path = True      # resident-state fast path of forward() (see the module docstring)
+
+    def invalidate(self):
+        """Forget the packed weights and the resident recurrent state: the next call re-packs both."""
+        self.param_sig = None
+        self._last = None
 
     # -- lifetime -------------------------------------------------------------------------
     def _ensure_handle(self):
@@ -144,7 +158,7 @@ class Engine:
         # The reference loop feeds every call the previous call's outputs (infer_BMCNet.py:61-64).  When the
         # arguments ARE those tensors, untouched, the states are still resident on the device: skip re-packing.
         given = list(hiddens) + [x_o_in]
-        resident = (not init) and self._last is not None and self._last[0] == (self.shape, self.param_sig) and \
+        resident = self.fast_path and (not init) and self._last is not None and self._last[0] == (self.shape, self.param_sig) and \
             len(given) == len(self._last[1]) and all(a is b and a._version == v for a, (b, v) in zip(given, self._last[1]))
         hp = [None] * 3 if resident else [p(t) for t in hs] + [None] * (3 - len(hs))
         op = [p(t) for t in outs] + [None] * (3 - len(outs))
