@@ -77,13 +77,19 @@ struct PerDevice {
 // prologue (barrier init, TMEM allocation, descriptor prefetch) and the launch latency overlap the previous
 // kernel's tail instead of sitting between the two.
 bool pdl_enabled();
+// Small launches (at most half the SMs get a CTA: batch-1 inference, infer_BMCNet.py:46-68) ARE launched with the
+// attribute: there the SMs are mostly idle, the successor's CTAs become resident at once and their prologues
+// (barrier init, TMEM allocation, descriptor prefetch, the weight-only part of the pipeline fill) run under the
+// predecessor's tail -- the step is a chain of ~23 / 54 dependent kernels of 15-30 CTAs each, and the gaps between
+// them are a large part of its latency.
+bool pdl_small_grid(unsigned ctas);
 template <class... KArgs, class... Args>
 inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    at[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() || pdl_small_grid(grid.x * grid.y * grid.z)) ? 1 : 0;
     cfg.attrs = at; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }

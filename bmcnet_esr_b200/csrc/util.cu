@@ -26,6 +26,12 @@ bool pdl_enabled() {
     return on != 0;
 }
 
+bool pdl_small_grid(unsigned ctas) {
+    static int on = -1;
+    if (on < 0) on = measure_env("BMC_PDL_SMALL", 1);        // measurement builds can switch the rule off for A/B runs
+    return on && 2 * (int)ctas <= sm_count();
+}
+
 int& PerDevice::cur() {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) dev = 0;
