@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
     const int tpc = p.tiles_per_cta, tpi = p.tiles_per_img;
     const int c_a = (img * tpi) / tpc, c_b = ((img + 1) * tpi - 1) / tpc;
     const int slot_a = segs_before(c_a, tpc, tpi, p.lcm) + (img - (c_a * tpc) / tpi);
-    const int n_slots = c_b - c_a + 1;
+    const int n_slots = p.pre_reduced ? 1 : c_b - c_a + 1;
     // All global reads are issued up front (they are pure latency: ~10 dependent L2 round trips otherwise).
     // Wv[c'][i] from the chunk-major fp16 matrix: row wv_row + (i/64)*128 + c', column i%64 (8 values per load)
     constexpr int kWl = 128 * 16 / kFoldThreads;      // Wv uint4 loads per thread
@@ -665,6 +665,41 @@ __global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// fold_prereduce: when an image's tiles were spread over MANY CTAs of bie_front_tc (small batches: at B = 1 every one of the
+// 31 tiles of a 45x80 image has its own CTA, hence 31 partial slots of 128 KB), the one CTA per (image, k) of att_fold
+// spent most of its time streaming the slots (39 us per launch at B = 1, a third of the whole batch-1 step).  This
+// kernel spreads that sum over 16 CTAs per (image, k): slot_a += slot_a+1 + ... in a FIXED order (deterministic), after
+// which att_fold reads a single slot (FoldParams::pre_reduced).  Launched only when an image has more than 3 slots.
+constexpr int kPreThreads = 256;
+__global__ void __launch_bounds__(kPreThreads) fold_prereduce(const FoldParams p) {
+    const int k = blockIdx.y & 1, img = blockIdx.y >> 1;
+    const int tpc = p.tiles_per_cta, tpi = p.tiles_per_img;
+    const int c_a = (img * tpi) / tpc, c_b = ((img + 1) * tpi - 1) / tpc;
+    const int slot_a = segs_before(c_a, tpc, tpi, p.lcm) + (img - (c_a * tpc) / tpi);
+    const int n_slots = c_b - c_a + 1;
+    pdl_wait();
+    pdl_launch_dependents();
+    if (n_slots <= 1) return;
+    float* g = const_cast<float*>(p.g_partial) + ((long)slot_a * 2 + k) * 128 * 128 + ((long)blockIdx.x * kPreThreads + threadIdx.x) * 4;
+    float4 a = *reinterpret_cast<const float4*>(g);
+    for (int s = 1; s < n_slots; s += 6) {
+        float4 t[6];
+#pragma unroll
+        for (int d = 0; d < 6; ++d)
+            t[d] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(g + (long)(s + d) * 2 * 128 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int d = 0; d < 6; ++d) { a.x += t[d].x; a.y += t[d].y; a.z += t[d].z; a.w += t[d].w; }
+    }
+    *reinterpret_cast<float4*>(g) = a;
+    if (blockIdx.x == 0 && threadIdx.x < 128) {
+        float* sp = const_cast<float*>(p.s_partial) + (long)slot_a * 256 + k * 128 + threadIdx.x;
+        float sv = sp[0];
+        for (int s = 1; s < n_slots; ++s) sv += sp[(long)s * 256];
+        sp[0] = sv;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // att_fold_tc: the same fold on the tensor core.  One CTA per (instance, image, k): all 128 rows c are the M of the
 //   MMAs, warp w post-processes rows 32 w .. 32 w + 31 (its TMEM lane quarter).  (A CTA per 32-row block used a
 //   quarter of every MMA, loaded Wv four times and ran the softmax on one warp.)  All 16 warps load G; the softmax is
@@ -704,7 +739,7 @@ __global__ void __launch_bounds__(kFoldTcThreads) att_fold_tc(const __grid_const
     const int tpc = p.tiles_per_cta, tpi = p.tiles_per_img;
     const int c_a = (img * tpi) / tpc, c_b = ((img + 1) * tpi - 1) / tpc;
     const int slot_a = segs_before(c_a, tpc, tpi, p.lcm) + (img - (c_a * tpc) / tpi);
-    const int n_slots = c_b - c_a + 1;
+    const int n_slots = p.pre_reduced ? 1 : c_b - c_a + 1;
 
     if (tid == 0) {
         mbar_init(&bar_w, 1); mbar_init(&bar_mma, 1);
@@ -920,7 +955,13 @@ int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream
         BMC_CUDA(cudaFuncSetAttribute(att_fold_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kFoldTcSmem));
         configured = 1;
     }
-    BMC_CUDA(launch_pdl(att_fold_tc, dim3(p.n_inst * p.B * 2 * (128 / kFoldTcRows)), dim3(kFoldTcThreads), (size_t)kFoldTcSmem, st, p, map_w));
+    FoldParams q = p;
+    q.pre_reduced = 0;
+    if (p.tiles_per_img > 3 * p.tiles_per_cta) {       // an image's partial sums sit in more than 3 slots
+        BMC_CUDA(launch_pdl(fold_prereduce, dim3(128 * 128 / 4 / kPreThreads, p.n_inst * p.B * 2), dim3(kPreThreads), (size_t)0, st, p));
+        q.pre_reduced = 1;
+    }
+    BMC_CUDA(launch_pdl(att_fold_tc, dim3(p.n_inst * p.B * 2 * (128 / kFoldTcRows)), dim3(kFoldTcThreads), (size_t)kFoldTcSmem, st, q, map_w));
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

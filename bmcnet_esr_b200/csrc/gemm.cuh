@@ -154,6 +154,7 @@ struct FoldParams {
     act_t* m_base;                         // per-image matrices: rows pair*B*256 + b*256 + chunk*128 + c, pair = inst*2 + k
     float* bias_img;                       // [pair][B][128]
     int dbg;                               // BMC_FOLD_PROF: print phase cycle counts
+    int pre_reduced;                       // fold_prereduce has summed each image's partial slots into its first one
 };
 int launch_bie_front(const BieFrontParams& p, cudaStream_t st);
 int launch_att_fold(const FoldParams& p, cudaStream_t st);                                   // SIMT version (BMC_FOLD_SIMT=1)
