@@ -62,6 +62,11 @@ struct GemmJobDev {
     signed char a_map32[kMaxSeg], t1_map32[kMaxSeg], w_map32;
     signed char out_map32;     // maps32 index of the OUTPUT tensor behind [32 rows x 64 ch] SWIZZLE_128B boxes (TMA-store epilogue), or -1
     int out_map_row;           // row of `out` inside that tensor
+    // conv_slab2_tc only: ADD the result onto the 16-bit tensor already in `out` (TMA reduce-add stores) instead of
+    // overwriting it: `identity + out` of ResidualBlock_noBN (submodules.py:35) when the block's output takes the slot of
+    // its input -- out = act16(x + act16(conv + bias)), one more 16-bit rounding than a single fp32 sum, no identity
+    // K segment, no residual read.  Only for launches whose OTHER operands do not include `out` with a spatial halo.
+    int out_accumulate;
 };
 
 struct alignas(64) GemmParams {
@@ -171,6 +176,7 @@ bool pair_supported(const GemmParams& p);
 bool slabt_supported(const GemmParams& p);
 int launch_conv_slabt(GemmParams p, cudaStream_t st);
 bool slab2_supported(const GemmParams& p);
+bool slab2_geom_supported(const Geom& g);
 int slab2_box_rows(const Geom& g, int n_taps);   // TMA box height conv_slab2_tc expects behind the activation maps32
 int launch_conv_slab2(GemmParams p, cudaStream_t st);
 int launch_conv_pair(GemmParams p, cudaStream_t st);

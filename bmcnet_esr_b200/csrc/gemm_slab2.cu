@@ -356,8 +356,13 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_slab2_tc(const __grid_const
                     asm volatile("bar.sync %0, 128;" ::"r"(3 + ph) : "memory");
                     if (leader) {
                         if (store_half) {
-                            tma_store_2d(omap, sbuf, 0, orow + c * 32);
-                            tma_store_2d(omap, sbuf + 4096, 64, orow + c * 32);
+                            if (job.out_accumulate) {        // out += tile: the ResidualBlock identity, added in L2 (gemm.cuh)
+                                tma_reduce_add_2d(omap, sbuf, 0, orow + c * 32);
+                                tma_reduce_add_2d(omap, sbuf + 4096, 64, orow + c * 32);
+                            } else {
+                                tma_store_2d(omap, sbuf, 0, orow + c * 32);
+                                tma_store_2d(omap, sbuf + 4096, 64, orow + c * 32);
+                            }
                         }
                         tma_store_commit();
                         tma_store_wait_read<1>();                             // the other buffer (chunk c - 1) has been read
@@ -488,6 +493,12 @@ static int slab2_smem(const Geom& g, int n_taps) {
     return kSlabStages * slab2_boxes(g, n_taps) * slab2_box_rows(g, n_taps) * kRowBytes + kWSlots * kWSlot + 32 * 1024 + 1024;
 }
 
+// geometry-only part of the test below: can a 3x3 128->128 launch at this image size run on this kernel at all?
+bool slab2_geom_supported(const Geom& g) {
+    if (!measure_env("BMC_CONV_SLAB2", 1)) return false;
+    return slab2_boxes(g, 9) <= 32 && slab2_smem(g, 9) + 2048 <= 227 * 1024;
+}
+
 bool slab2_supported(const GemmParams& p) {
     static int enabled = -1;
     if (enabled < 0) enabled = measure_env("BMC_CONV_SLAB2", 1);
@@ -498,6 +509,7 @@ bool slab2_supported(const GemmParams& p) {
     for (int j = 0; j < p.n_jobs; ++j) {
         const GemmJobDev& d = p.jobs[j];
         if (d.w_img_stride != 0 || d.residual || d.out_f32 || d.ln_gamma || !d.out || d.w_map32 < 0) return false;
+        if (d.out_accumulate && d.out_map32 < 0) return false;      // the in-place add exists only in the TMA-store epilogue
         for (int s = 0; s < p.n_seg; ++s) {
             if (d.a_map32[s] < 0) return false;
             if (((p.tap1_mask >> s) & 1) && d.t1_map32[s] < 0) return false;

@@ -282,6 +282,11 @@ int launch_conv_gemm(const GemmParams& p, int impl, cudaStream_t st) {
     // conv_slab2_tc wins on launches made of 3x3 segments only; launches with centre-tap segments (one short
     // phase per 32 channels, each with its own slab) are faster on conv_slabt_tc (measured)
     if (impl == 0 && !p.tap1_mask && slab2_supported(p)) return launch_conv_slab2(p, st);
+    for (int j = 0; j < p.n_jobs; ++j)
+        if (p.jobs[j].out_accumulate) {
+            set_error("conv_gemm: an accumulating output (in-place residual add) exists only in conv_slab2_tc");
+            return BMC_ERR_UNSUPPORTED;
+        }
     if (impl == 0 && p.jobs[0].a_map64[0] >= 0 && slab_supported(p) && slabt_supported(p)) return launch_conv_slabt(p, st);
     if (p.tap1_mask) return launch_conv_slab(p, st);
     if (impl == 1) return launch_conv_gemm_simt(p, st);

@@ -134,6 +134,7 @@ struct JobSpec {
     // centre-tap-only segments appended after `segs` (slab kernel only, gemm.cuh GemmJobDev::t1_*):
     int mix_slot = -1, mix_pair = -1;   // + M_pair[b] . x  with x in arena slot mix_slot (fused BIE, bie_fused.cu)
     int ident_slot = -1;                // + I . x : a residual add done by the tensor core
+    bool accumulate = false;            // out_slot already holds the residual: add the result onto it (conv_slab2_tc reduce-add epilogue)
 };
 
 struct Op {
@@ -167,6 +168,7 @@ struct bmc_model {
     size_t off_mi = 0, off_a32 = 0, off_p = 0, off_partial = 0, off_hid32 = 0, off_bimg = 0, off_gpart = 0, off_spart = 0;
     bool fused = true;                     // product plan: fused BIE 1x1 / attention section (bie_fused.cu)
     bool allow_fused = true;
+    bool inplace_res = true;               // ResidualBlock identity as an in-place reduce-add (needs conv_slab2_tc at this image size)
     char* ws = nullptr;
     CUtensorMap map_act, map_att, map_slab, map_mi, map_mi64, map_w128, map_w64, map_w32, map_p;
     CUtensorMap map_act_s64, map_mi_s64, map_w_s64, map_p_s64;   // 32-channel / 64-byte-swizzle boxes (conv_slab2_tc)
@@ -372,6 +374,7 @@ struct Builder {
             d.out_map32 = js.out_slot >= 0 ? 4 : -1;
             d.out_map_row = js.out_slot >= 0 ? (int)(js.out_slot * g.rows()) : 0;
             d.out_f32 = js.out_f32 ? m->a32_ptr() : nullptr;
+            d.out_accumulate = js.accumulate ? 1 : 0;
             if (js.ln >= 0) {
                 d.ln_gamma = m->f32_dev + m->lns[js.ln].gamma_off;
                 d.ln_beta = m->f32_dev + m->lns[js.ln].beta_off;
@@ -611,12 +614,21 @@ struct Builder {
             gemm(jobs, 128, 9);
             jobs.assign(4, JobSpec());
             for (int j = 0; j < 4; ++j) {
-                xo[j] = alloc();
-                jobs[j].segs = {{0, t[j]}}; jobs[j].weight = W(p + nm[j] + ".conv2"); jobs[j].out_slot = xo[j];
-                if (m->fused) jobs[j].ident_slot = xin[j]; else jobs[j].res_slot = xin[j];
+                jobs[j].segs = {{0, t[j]}}; jobs[j].weight = W(p + nm[j] + ".conv2");
+                if (m->fused && m->inplace_res) {
+                    // x + conv2(relu(conv1(x))) IN PLACE: the launch is a plain 3x3 convolution of t whose epilogue adds
+                    // the result onto x in its own slot (TMA reduce-add): no identity K segment (it cost 59 us per
+                    // launch on conv_slabt_tc), the launch runs on the two-tile kernel
+                    xo[j] = xin[j];
+                    jobs[j].out_slot = xo[j]; jobs[j].accumulate = true;
+                } else {
+                    xo[j] = alloc();
+                    jobs[j].out_slot = xo[j];
+                    if (m->fused) jobs[j].ident_slot = xin[j]; else jobs[j].res_slot = xin[j];
+                }
             }
             gemm(jobs, 128, 9);
-            for (int j = 0; j < 4; ++j) { release(t[j]); release(xin[j]); }
+            for (int j = 0; j < 4; ++j) { release(t[j]); if (xo[j] != xin[j]) release(xin[j]); }
             // ... local BIE on each polarity (shared weights), then the global BIE across them
             auto l = bie(p + ".lBIE", {{xo[0], xo[2], xs_p}, {xo[1], xo[3], xs_n}});
             xp_st = l[0].x2; xs_p = l[0].xs; xn_st = l[1].x2; xs_n = l[1].xs;
@@ -881,6 +893,7 @@ extern "C" BMC_EXPORT int bmc_model_configure(bmc_model_t* m, int batch, int H, 
         memset(&probe, 0, sizeof(probe));
         probe.n = 128; probe.n_taps = 9; probe.g = m->g;
         m->allow_fused = slab_supported(probe) && measure_env("BMC_FUSED", 1);
+        m->inplace_res = slab2_geom_supported(m->g);
     }
     Builder b{m};
     m->fused = false;
