@@ -658,6 +658,15 @@ def main():
                 del cx.models[name]
                 torch.cuda.empty_cache()
         extra['bmcnet_train_nfs'] = run_train(cx)
+        if world == 1:
+            # the reference's batch (2) leaves the iteration host-bound (Python autograd tape); a larger batch shows
+            # what the kernels sustain
+            try:
+                big = run_train(cx, batch=8, iters=2)
+                extra['bmcnet_train_nfs']['batch_8'] = {k: big[k] for k in ('value', 'unit', 'ms_per_iteration', 'batch_per_gpu', 'loss_finite')}
+            except torch.cuda.OutOfMemoryError:
+                extra['bmcnet_train_nfs']['batch_8'] = {'unavailable': 'out of memory'}
+            torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:

@@ -62,6 +62,8 @@ SIGNATURES = {
     'bmc_conv_wgrad_workspace_bytes': (_sz, [_i, _i, _i]),
     'bmc_conv_wgrad': (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _f, _vp, _vp, _vp, _sz, _i, _vp]),
     'bmc_relu_backward': (_i, [_vp, _vp, _i64, _vp, _vp]),
+    'bmc_layernorm_rows_backward_workspace_bytes': (_sz, []),
+    'bmc_layernorm_rows_backward': (_i, [_vp, _vp, _vp, _f, _i64, _vp, _f, _vp, _vp, _vp, _sz, _vp]),
     'bmc_adam_amsgrad_step': (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _f, _f, _f, _f, _f, _vp]),
 }
 

@@ -180,6 +180,67 @@ __global__ void relu_backward(const uint32_t* __restrict__ dy, const uint32_t* _
     dx[i] = pack_act2(v.x > 0.f ? g.x : 0.f, v.y > 0.f ? g.y : 0.f);
 }
 
+// LayerNormFunction.backward (submodules.py:142-154) on packed rows: one warp per row, 4 channels per lane.
+//   y_hat = (x - mu) * rstd ; g = dy * gamma ; dx = rstd * (g - y_hat * mean(g * y_hat) - mean(g))
+//   dgamma = sum_rows dy * y_hat ; dbeta = sum_rows dy          (per-CTA partials, reduced in a fixed order)
+// mu / rstd are recomputed from x (fp32 math on the 16-bit input, like the forward kernel in pointwise.cu).
+constexpr int kLnbThreads = 256;                 // 8 rows per pass
+__global__ void __launch_bounds__(kLnbThreads) layernorm_backward(const act_t* __restrict__ x, const act_t* __restrict__ dy,
+                                                                  const float* __restrict__ gamma, float eps, long rows,
+                                                                  act_t* __restrict__ dx, float* __restrict__ partial) {
+    __shared__ float s_g[8][128], s_b[8][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 gm = *reinterpret_cast<const float4*>(gamma + lane * 4);
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+    for (long row = (long)blockIdx.x * 8 + warp; row < rows; row += (long)gridDim.x * 8) {
+        const uint2 xr = *reinterpret_cast<const uint2*>(x + row * 128 + lane * 4);
+        const uint2 dr = *reinterpret_cast<const uint2*>(dy + row * 128 + lane * 4);
+        const float2 x0 = unpack_act2(xr.x), x1 = unpack_act2(xr.y), d0 = unpack_act2(dr.x), d1 = unpack_act2(dr.y);
+        const float xv[4] = {x0.x, x0.y, x1.x, x1.y}, dv[4] = {d0.x, d0.y, d1.x, d1.y};
+        float s = xv[0] + xv[1] + xv[2] + xv[3];
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mu = s * (1.f / 128.f);
+        float v = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v += (xv[j] - mu) * (xv[j] - mu);
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        const float rstd = 1.f / sqrtf(v * (1.f / 128.f) + eps);
+        const float gv[4] = {gm.x, gm.y, gm.z, gm.w};
+        float yh[4], g[4], sg = 0.f, sgy = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            yh[j] = (xv[j] - mu) * rstd;
+            g[j] = dv[j] * gv[j];
+            sg += g[j];
+            sgy += g[j] * yh[j];
+            ag[j] += dv[j] * yh[j];
+            ab[j] += dv[j];
+        }
+        for (int o = 16; o; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sgy += __shfl_xor_sync(0xffffffffu, sgy, o); }
+        const float mg = sg * (1.f / 128.f), mgy = sgy * (1.f / 128.f);
+        uint2 o2;
+        o2.x = pack_act2(rstd * (g[0] - yh[0] * mgy - mg), rstd * (g[1] - yh[1] * mgy - mg));
+        o2.y = pack_act2(rstd * (g[2] - yh[2] * mgy - mg), rstd * (g[3] - yh[3] * mgy - mg));
+        *reinterpret_cast<uint2*>(dx + row * 128 + lane * 4) = o2;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_g[warp][lane * 4 + j] = ag[j]; s_b[warp][lane * 4 + j] = ab[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w) { a += s_g[w][threadIdx.x]; b += s_b[w][threadIdx.x]; }
+        partial[(long)blockIdx.x * 256 + threadIdx.x] = a;
+        partial[(long)blockIdx.x * 256 + 128 + threadIdx.x] = b;
+    }
+}
+__global__ void layernorm_backward_reduce(const float* __restrict__ partial, int n, float scale, float* __restrict__ dgamma,
+                                          float* __restrict__ dbeta) {
+    const int c = threadIdx.x;                   // 256 threads: 0..127 gamma, 128..255 beta
+    float s = 0.f;
+    for (int k = 0; k < n; ++k) s += partial[(long)k * 256 + c];
+    if (c < 128) dgamma[c] += scale * s; else dbeta[c - 128] += scale * s;
+}
+
 // torch.optim.Adam(amsgrad=True) with L2 weight decay (config/train_nfs.yml:28-34), one step over flat buffers:
 //   g = grad + wd * p ; m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; vmax = max(vmax, v)
 //   p -= lr / (1 - b1^t) * m / (sqrt(vmax) / sqrt(1 - b2^t) + eps)
@@ -278,6 +339,26 @@ extern "C" BMC_EXPORT int bmc_adam_amsgrad_step(float* params, const float* grad
     const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
     adam_amsgrad<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(params, grads, exp_avg, exp_avg_sq, max_exp_avg_sq,
                                                                               (long)n, lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt);
+    BMC_CUDA(cudaGetLastError());
+    return BMC_OK;
+}
+
+extern "C" BMC_EXPORT size_t bmc_layernorm_rows_backward_workspace_bytes(void) { return (size_t)296 * 256 * sizeof(float); }
+
+extern "C" BMC_EXPORT int bmc_layernorm_rows_backward(const void* x_act16, const void* dy_act16, const float* gamma, float eps,
+                                                      int64_t rows, void* dx_act16, float scale, float* grad_gamma,
+                                                      float* grad_beta, void* workspace, size_t workspace_bytes, void* stream) {
+    BMC_REQUIRE(x_act16 && dy_act16 && gamma && dx_act16 && grad_gamma && grad_beta && workspace && rows >= 0,
+                "layernorm_rows_backward: bad argument");
+    BMC_REQUIRE(workspace_bytes >= bmc_layernorm_rows_backward_workspace_bytes(), "layernorm_rows_backward: workspace too small");
+    if (rows == 0) return BMC_OK;
+    cudaStream_t st = as_stream(stream);
+    long want = (rows + 7) / 8;
+    const int grid = (int)(want < 296 ? want : 296);
+    float* partial = static_cast<float*>(workspace);
+    layernorm_backward<<<grid, kLnbThreads, 0, st>>>(static_cast<const act_t*>(x_act16), static_cast<const act_t*>(dy_act16), gamma,
+                                                     eps, (long)rows, static_cast<act_t*>(dx_act16), partial);
+    layernorm_backward_reduce<<<1, 256, 0, st>>>(partial, grid, scale, grad_gamma, grad_beta);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

@@ -151,3 +151,14 @@ def conv_wgrad(dy, x, taps, b, h, w, cmap, cin_total, n_out, scale, grad_w, grad
         check(lib().bmc_conv_wgrad(dy.data_ptr(), x.data_ptr(), x.shape[1], taps, b, h, w, cmap.data_ptr(), cin_total,
                                    n_out, scale, grad_w.data_ptr(), grad_b.data_ptr() if grad_b is not None else None,
                                    workspace.data_ptr(), workspace.numel(), n_split, stream_ptr()))
+
+
+def layernorm_rows_backward(x, dy, gamma, eps, scale, grad_gamma, grad_beta, workspace):
+    """dx of the channel LayerNorm (bmc_layernorm_rows_backward); grad_gamma / grad_beta (fp32 [128]) += scale * sums."""
+    dx = torch.empty_like(dy)
+    g = gamma.contiguous().float()
+    with _need_cuda(x, dy, g, grad_gamma, grad_beta, workspace):
+        check(lib().bmc_layernorm_rows_backward(x.data_ptr(), dy.data_ptr(), g.data_ptr(), eps, x.shape[0], dx.data_ptr(), scale,
+                                                grad_gamma.data_ptr(), grad_beta.data_ptr(), workspace.data_ptr(),
+                                                workspace.numel(), stream_ptr()))
+    return dx

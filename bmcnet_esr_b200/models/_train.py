@@ -12,8 +12,9 @@ is recording, `BMCNet.forward` / `BMCNet_plain.forward` route to this module, wh
       wgrad     bmc_conv_wgrad (csrc/train.cu: tcgen05 split-K over pixels, fp32, accumulated straight into
                 `param.grad` -- aliased modules share one Parameter, hence one gradient buffer)
       ReLU'     bmc_relu_backward
-  the small rest (channel LayerNorm, the 128x128 attention bmm/softmax, residual adds, pixel (un)shuffle, bilinear
-  base, MSE) is ordinary differentiable PyTorch on the padded-NHWC tensors, in fp32 where it matters.
+  channel LayerNorm (norm_s of every BIE, submodules.py:127-166): bmc_layernorm_rows / bmc_layernorm_rows_backward
+  the small rest (the 128x128 attention bmm/softmax, residual adds, pixel (un)shuffle, bilinear base, MSE) is ordinary
+  differentiable PyTorch on the padded-NHWC tensors, in fp32 where it matters.
 
 Activations and activation gradients are act16 (fp16 in the default build); weight gradients accumulate in fp32.
 fp16 gradients of a mean-reduced MSE over 10^5 outputs (~1e-6) would underflow, so the whole 16-bit region runs under a
@@ -205,13 +206,28 @@ def resblock(tc, m, x, geom):
     return x + conv(tc, m.conv2, [t], [_R128], geom)
 
 
-def layernorm_rows(y, weight, bias, eps):
-    """LayerNorm2d over channels on packed rows (submodules.py:127-139), fp32 math."""
-    yf = y.float()
-    mu = yf.mean(1, keepdim=True)
-    d = yf - mu
-    var = (d * d).mean(1, keepdim=True)
-    return (weight.view(1, -1) * (d / (var + eps).sqrt()) + bias.view(1, -1)).to(y.dtype)
+class _LayerNormFn(torch.autograd.Function):
+    """LayerNorm2d / LayerNormFunction (submodules.py:127-166) on packed rows: forward = bmc_layernorm_rows, backward =
+    bmc_layernorm_rows_backward (dx; dgamma / dbeta accumulated into `.grad`, un-scaled, like the conv weights)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, tc, norm):
+        x = x.contiguous()
+        ctx.tc, ctx.norm = tc, norm
+        ctx.save_for_backward(x)
+        return K.layernorm_rows(x, norm.weight.detach(), norm.bias.detach(), norm.eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        tc, norm = ctx.tc, ctx.norm
+        dx = K.layernorm_rows_backward(x, dy.contiguous(), norm.weight.detach(), norm.eps, 1.0 / tc.loss_scale,
+                                       _grad_buf(norm.weight), _grad_buf(norm.bias), tc.workspace(x.device))
+        return dx, None, None, None
+
+
+def layernorm_rows(tc, norm, y):
+    return _LayerNormFn.apply(y, norm.weight, tc, norm)
 
 
 def bie(tc, m, x1, x2, xs, geom):
@@ -220,13 +236,11 @@ def bie(tc, m, x1, x2, xs, geom):
     r = K.rows_per_image(h, w)
     r1 = resblock(tc, m.conv1, x1, geom)
     r2 = resblock(tc, m.conv2, x2, geom)
-    s = 1.0 / tc.loss_scale
-    gamma, beta = _ScaleGrad.apply(m.norm_s.weight, s), _ScaleGrad.apply(m.norm_s.bias, s)
     two = [_R128, _seg(128)]
 
     def centre(convf, other):
         u = conv(tc, convf, [xs, other], two, geom)
-        return conv(tc, m.clustering, [layernorm_rows(u, gamma, beta, m.norm_s.eps)], [_R128], geom)
+        return conv(tc, m.clustering, [layernorm_rows(tc, m.norm_s, u)], [_R128], geom)
 
     c1, c2 = centre(m.convf1, x2), centre(m.convf2, x1)
     v1 = conv(tc, m.v1, [x1], [_R128], geom)

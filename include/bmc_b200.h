@@ -305,6 +305,13 @@ int bmc_conv_wgrad(const void* dy_act16, const void* x_act16, int x_ch, int taps
                    const int* cmap, int cin_total, int n_out, float scale, float* grad_w, float* grad_b,
                    void* workspace, size_t workspace_bytes, int n_split, void* stream);
 int bmc_relu_backward(const void* dy_act16, const void* y_act16, int64_t n_elems, void* dx_act16, void* stream);
+/* LayerNormFunction.backward (submodules.py:142-154) for bmc_layernorm_rows: dx (act16 [rows][128]) from x and dy;
+ * grad_gamma[c] += scale * sum_rows dy * y_hat, grad_beta[c] += scale * sum_rows dy (device float[128], ACCUMULATED;
+ * per-CTA partials reduced in a fixed order).  mu / rstd are recomputed from x. */
+size_t bmc_layernorm_rows_backward_workspace_bytes(void);
+int bmc_layernorm_rows_backward(const void* x_act16, const void* dy_act16, const float* gamma, float eps, int64_t rows,
+                                void* dx_act16, float scale, float* grad_gamma, float* grad_beta, void* workspace,
+                                size_t workspace_bytes, void* stream);
 int bmc_adam_amsgrad_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                           float* max_exp_avg_sq, int64_t n, int step, float lr, float beta1, float beta2,
                           float eps, float weight_decay, void* stream);

@@ -95,6 +95,36 @@ def test_residual_block_backward_end_to_end():
         assert _rel_max(p.grad, ps[n].grad) <= 1e-2, (n, _rel_max(p.grad, ps[n].grad))
 
 
+def test_layernorm_backward_kernel_vs_autograd():
+    """LayerNormFunction.backward (submodules.py:142-154): dx, dgamma, dbeta of the channel LayerNorm kernel pair against
+    torch.autograd on the fp32 formula, on fp16-rounded inputs (14,000 rows incl. rows of all zeros like the halo)."""
+    from bmcnet_esr_b200.models import _train as TR
+    from bmcnet_esr_b200.models.submodules import LayerNorm2d
+    torch.manual_seed(5)
+    rows = 14000
+    norm = LayerNorm2d(128).cuda()
+    with torch.no_grad():
+        norm.weight.copy_(0.87 + 0.05 * torch.randn(128))
+        norm.bias.copy_(0.03 * torch.randn(128))
+    x = (torch.randn(rows, 128, device='cuda') * 1.5 + 0.3).half()
+    x[::97] = 0
+    xg = x.clone().requires_grad_(True)
+    tc = TR._Ctx(8.0)
+    y = TR.layernorm_rows(tc, norm, xg)
+    gy = (torch.randn(rows, 128, device='cuda') * 0.5).half()
+    y.backward(gy)
+    xr = x.float().requires_grad_(True)
+    g, b = norm.weight.detach().clone().requires_grad_(True), norm.bias.detach().clone().requires_grad_(True)
+    mu = xr.mean(1, keepdim=True)
+    var = ((xr - mu) ** 2).mean(1, keepdim=True)
+    yr = g * ((xr - mu) / (var + norm.eps).sqrt()) + b
+    yr.backward(gy.float())
+    assert _rel_max(y.detach().float(), yr.detach()) <= 2e-3
+    assert _rel_l2(xg.grad.float(), xr.grad) <= 2e-3, _rel_l2(xg.grad.float(), xr.grad)
+    # (the loss scale of the context divides the parameter gradients: 8.0)
+    assert _rel_max(norm.weight.grad * 8.0, g.grad) <= 2e-3 and _rel_max(norm.bias.grad * 8.0, b.grad) <= 2e-3
+
+
 def test_adam_amsgrad_kernel_matches_update_rule():
     from bmcnet_esr_b200.models._train import FusedAdamAMSGrad
     torch.manual_seed(0)

@@ -1,5 +1,5 @@
-"""Host logic of the training path (bmcnet_esr_b200/models/_train.py) WITHOUT a GPU: the three kernels it calls
-(bmc_conv_gemm, bmc_conv_wgrad, bmc_relu_backward, reached through kernels.py) are replaced by plain-torch fp32
+"""Host logic of the training path (bmcnet_esr_b200/models/_train.py) WITHOUT a GPU: the kernels it calls
+(bmc_conv_gemm, bmc_conv_wgrad, bmc_relu_backward, bmc_layernorm_rows and its backward, reached through kernels.py) are replaced by plain-torch fp32
 stand-ins of their documented contracts (include/bmc_b200.h), and the resulting loss / gradients of a whole
 BPTT sequence are compared with the fp32 autograd oracle (oracle/train_step.py, itself pinned to the reference's
 modules + nn.MSELoss + torch.optim.Adam).  What this pins: the autograd wiring, the K-segment channel maps of every
@@ -75,6 +75,27 @@ def fake_relu_backward(dy, y):
     return dy * (y > 0)
 
 
+def fake_layernorm_rows(a, gamma, beta, eps):
+    x = a.float()
+    mu = x.mean(1, keepdim=True)
+    var = ((x - mu) ** 2).mean(1, keepdim=True)
+    return (gamma.view(1, -1) * ((x - mu) / (var + eps).sqrt()) + beta.view(1, -1)).to(a.dtype)
+
+
+def fake_layernorm_rows_backward(x, dy, gamma, eps, scale, grad_gamma, grad_beta, workspace):
+    """submodules.py:142-154"""
+    xf, d = x.float(), dy.float()
+    mu = xf.mean(1, keepdim=True)
+    var = ((xf - mu) ** 2).mean(1, keepdim=True)
+    rstd = 1.0 / (var + eps).sqrt()
+    yh = (xf - mu) * rstd
+    g = d * gamma.view(1, -1)
+    dx = rstd * (g - yh * (g * yh).mean(1, keepdim=True) - g.mean(1, keepdim=True))
+    grad_gamma += scale * (d * yh).sum(0)
+    grad_beta += scale * d.sum(0)
+    return dx.to(dy.dtype)
+
+
 @pytest.fixture
 def fake_kernels(monkeypatch):
     from bmcnet_esr_b200 import _lib, kernels as K
@@ -82,6 +103,8 @@ def fake_kernels(monkeypatch):
     monkeypatch.setattr(K, 'conv_gemm', fake_conv_gemm)
     monkeypatch.setattr(K, 'conv_wgrad', fake_conv_wgrad)
     monkeypatch.setattr(K, 'relu_backward', fake_relu_backward)
+    monkeypatch.setattr(K, 'layernorm_rows', fake_layernorm_rows)
+    monkeypatch.setattr(K, 'layernorm_rows_backward', fake_layernorm_rows_backward)
 
 
 def _grads_of(model):
