@@ -668,10 +668,12 @@ __global__ void __launch_bounds__(kFoldThreads) att_fold(const FoldParams p) {
 // fold_prereduce: when an image's tiles were spread over MANY CTAs of bie_front_tc (small batches: at B = 1 every one of the
 // 31 tiles of a 45x80 image has its own CTA, hence 31 partial slots of 128 KB), the one CTA per (image, k) of att_fold
 // spent most of its time streaming the slots (39 us per launch at B = 1, a third of the whole batch-1 step).  This
-// kernel spreads that sum over 16 CTAs per (image, k): slot_a += slot_a+1 + ... in a FIXED order (deterministic), after
+// kernel spreads that sum over 64 CTAs per (image, k): slot_a += slot_a+1 + ... in a FIXED order (deterministic), after
 // which att_fold reads a single slot (FoldParams::pre_reduced).  Launched only when an image has more than 3 slots.
 constexpr int kPreThreads = 256;
+constexpr int kPreCols = 64;                     // float4 columns per CTA; the 4 thread groups of a CTA take every 4th slot
 __global__ void __launch_bounds__(kPreThreads) fold_prereduce(const FoldParams p) {
+    __shared__ float4 s_part[3][kPreCols];
     const int k = blockIdx.y & 1, img = blockIdx.y >> 1;
     const int tpc = p.tiles_per_cta, tpi = p.tiles_per_img;
     const int c_a = (img * tpi) / tpc, c_b = ((img + 1) * tpi - 1) / tpc;
@@ -680,17 +682,26 @@ __global__ void __launch_bounds__(kPreThreads) fold_prereduce(const FoldParams p
     pdl_wait();
     pdl_launch_dependents();
     if (n_slots <= 1) return;
-    float* g = const_cast<float*>(p.g_partial) + ((long)slot_a * 2 + k) * 128 * 128 + ((long)blockIdx.x * kPreThreads + threadIdx.x) * 4;
-    float4 a = *reinterpret_cast<const float4*>(g);
-    for (int s = 1; s < n_slots; s += 6) {
-        float4 t[6];
+    const int grp = threadIdx.x / kPreCols, col = threadIdx.x % kPreCols;
+    float* g = const_cast<float*>(p.g_partial) + ((long)slot_a * 2 + k) * 128 * 128 + ((long)blockIdx.x * kPreCols + col) * 4;
+    // group `grp` sums slots grp, grp + 4, ... (all loads of a batch of 8 in flight); the groups are then added in the
+    // fixed order 0, 1, 2, 3: the same bits on every run
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = grp; s < n_slots; s += 32) {
+        float4 t[8];
 #pragma unroll
-        for (int d = 0; d < 6; ++d)
-            t[d] = (s + d < n_slots) ? *reinterpret_cast<const float4*>(g + (long)(s + d) * 2 * 128 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int d = 0; d < 8; ++d)
+            t[d] = (s + 4 * d < n_slots) ? *reinterpret_cast<const float4*>(g + (long)(s + 4 * d) * 2 * 128 * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int d = 0; d < 6; ++d) { a.x += t[d].x; a.y += t[d].y; a.z += t[d].z; a.w += t[d].w; }
+        for (int d = 0; d < 8; ++d) { a.x += t[d].x; a.y += t[d].y; a.z += t[d].z; a.w += t[d].w; }
     }
-    *reinterpret_cast<float4*>(g) = a;
+    if (grp > 0) s_part[grp - 1][col] = a;
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { const float4 t = s_part[d][col]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+        *reinterpret_cast<float4*>(g) = a;
+    }
     if (blockIdx.x == 0 && threadIdx.x < 128) {
         float* sp = const_cast<float*>(p.s_partial) + (long)slot_a * 256 + k * 128 + threadIdx.x;
         float sv = sp[0];
@@ -958,7 +969,7 @@ int launch_att_fold_tc(const FoldParams& p, const CUtensorMap& map_w, cudaStream
     FoldParams q = p;
     q.pre_reduced = 0;
     if (p.tiles_per_img > 3 * p.tiles_per_cta) {       // an image's partial sums sit in more than 3 slots
-        BMC_CUDA(launch_pdl(fold_prereduce, dim3(128 * 128 / 4 / kPreThreads, p.n_inst * p.B * 2), dim3(kPreThreads), (size_t)0, st, p));
+        BMC_CUDA(launch_pdl(fold_prereduce, dim3(128 * 128 / 4 / kPreCols, p.n_inst * p.B * 2), dim3(kPreThreads), (size_t)0, st, p));
         q.pre_reduced = 1;
     }
     BMC_CUDA(launch_pdl(att_fold_tc, dim3(p.n_inst * p.B * 2 * (128 / kFoldTcRows)), dim3(kFoldTcThreads), (size_t)kFoldTcSmem, st, q, map_w));
