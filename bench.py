@@ -65,12 +65,13 @@ WORKLOADS = {
 # BMCNet 5.86k / 6.11k / 6.21k at B = 38 / 57 / 76)
 DEFAULT_BATCH = {'plain_nfs': 95, 'bmcnet_nfs': 76, 'bmcnet_eventzoom': 156}
 CONV_MAC_PER_PX = 147456          # 3x3 128->128
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r01_ncu_full_*.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from `ncu --set full` (profiles/r0?_ncu_full_*.txt):
 # conv_slab2_tc, 2 jobs, 45x80: B=95: 193.4 + 143.0 MB (algorithmic 193.0 read + 193.0 written; part of the output is
 # still dirty in L2 when the kernel ends), B=57: 116.2 + 70.5 MB; encoders: bytes per event at 1e8 events
 # (12.04 / 16.04 for 12 / 16 algorithmic)
-NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): 336.4e6, ('plain', 57, 45, 80): 186.7e6,
-                    ('full', 76, 45, 80): 569.8e6}       # 4 jobs, B=76: 309.2 MB read + 260.5 MB written
+NCU_CONV_TRAFFIC = {('plain', 95, 45, 80): (337.9e6, 'profiles/r02_ncu_full_slab2_plain3x3.txt'),     # 193.5 MB read + 144.5 MB written
+                    ('plain', 57, 45, 80): (186.7e6, 'profiles/r01_B57_B38/'),
+                    ('full', 76, 45, 80): (569.8e6, 'profiles/r01_ncu_full_slab2_bmcnet3x3.txt')}    # 4 jobs: 309.2 MB read + 260.5 MB written
 NCU_ENC_BYTES_PER_EVENT, NCU_VOX_BYTES_PER_EVENT = 12.045, 16.035
 FLOP_PER_PX = {'plain': 9721856, 'full': 41574912}      # SURVEY 8d / BASELINE.md section 3
 SUSTAINED_SECONDS = 2.0
@@ -541,7 +542,8 @@ def conv_roofline(cx, model_kind, B, h, w, peaks):
     peak = peaks.get('bf16_tflops', 1590.0)
     return {'kernel': 'conv_slab2_tc (3x3 128->128 implicit GEMM, %d jobs, B=%d)' % (jobs, B), 'bound': 'tensor',
             'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-            'traffic': NCU_CONV_TRAFFIC.get((model_kind, B, h, w)), 'traffic_unit': 'bytes per launch (ncu, profiles/r01_ncu_full_slab2_%s3x3.txt)' % ('plain' if model_kind == 'plain' else 'bmcnet'),
+            'traffic': NCU_CONV_TRAFFIC.get((model_kind, B, h, w), (None, None))[0],
+            'traffic_unit': 'bytes per launch (ncu --set full, %s)' % NCU_CONV_TRAFFIC.get((model_kind, B, h, w), (None, 'no capture at this shape'))[1],
             'algorithmic_bytes': 2.0 * jobs * B * (((h + 2) * (w + 2) + 127) // 128 * 128) * 128 * 2,   # input read + output written
             'us_per_launch': conv_ms * 1e3,
             'peak_source': 'MEASURED_PEAKS.json bf16_tflops (burst; kernel timed alone)' if peaks else 'fallback 1.59 PFLOP/s (B200_PROFILING.md; MEASURED_PEAKS.json absent)'}

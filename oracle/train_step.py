@@ -10,8 +10,9 @@ modules do.
 
 Pinned by oracle/make_golden.py::make_train_goldens against the reference's own nn.Modules + nn.MSELoss +
 torch.optim.Adam run in this container (tests/golden/train_step_*.npz; tests/test_oracle_vs_golden.py).
-No CUDA kernel of this repo implements the backward yet: this file and its goldens are the oracle the
-round-2 kernels will be checked against.
+The CUDA training path (bmcnet_esr_b200/models/_train.py, csrc/train.cu) is checked against this file in
+tests/test_train_graph_cpu.py (host logic, CPU) and tests/test_gpu_train*.py (kernels).  Both reference trainers
+(/root/reference/train.py and train_plain.py) run the same iteration.
 """
 import torch
 import torch.nn.functional as F
