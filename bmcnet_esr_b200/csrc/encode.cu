@@ -19,7 +19,16 @@ constexpr int kSmemBudget = 227 * 1024;        // dynamic smem per CTA on sm_100
 constexpr int kMaxBinsSmem32 = 49152;          // 192 KB of int32 / fp32 bins
 constexpr int kMaxBinsSmem16 = kSmemBudget / 2;  // 16-bit packed bins
 
-enum Mode { kSmem32 = 0, kSmem16 = 1, kGlobal = 2, kSmem64 = 3, kGlobal64 = 4 };
+enum Mode { kSmem32 = 0, kSmem16 = 1, kGlobal = 2, kSmem64 = 3, kGlobal64 = 4, kSmemFix = 5 };
+// kSmemFix: the default path of the float-weighted encoders on grids that fit (2 x bins x 4 B <= 227 KB).  Every weight is
+// split by sign and added as UNSIGNED 2^-24 fixed point to one of two 32-bit shared-memory bins (positive / negative
+// plane) with a native ATOMS.ADD; the thread whose add wraps a bin (the returned old value tells it: exactly one thread
+// per wrap) credits 2^32 to the global 64-bit grid.  No compare-and-swap loops (an fp32 shared-memory atomicAdd compiles to
+// ATOMS.CAST.SPIN: LDS + FADD + CAS + branch per attempt), integer sums only -- so the result does not depend on the order
+// the atomics land in (bit-reproducible), and a weight's rounding error is <= 2^-25 (fp32's own resolution for weights in
+// [0.5, 1)).  |weight| >= 128 (never the case for +-1 polarities) goes to the 64-bit grid directly.
+constexpr int kFixBits = 24;
+constexpr int kMaxBinsSmemFix = kSmemBudget / 8;
 constexpr int kMaxBinsSmem64 = 24576;          // 192 KB of 64-bit fixed-point bins
 
 // BMC_ENC_DETERMINISTIC: float weights are accumulated as 64-bit fixed point (2^-32 units).  Integer addition is
@@ -58,12 +67,14 @@ __device__ __forceinline__ Pix decode_xy(float x, float y, int H, int W, bool fl
 // ---------------------------------------------------------------- accumulation targets
 template <int MODE, bool FLOAT_HIST>
 struct Hist {
+    static constexpr int kMode = MODE;
     int* s_i;        // smem int32 bins / packed 16-bit pairs
     float* s_f;      // smem fp32 bins (FLOAT_HIST)
     int* g_cnt;      // global int32 grid
     float* g_ext;    // global fp32 grid (non-integral weights)
     unsigned long long* s64;   // kSmem64: smem fixed-point bins
-    unsigned long long* g64;   // kSmem64 / kGlobal64: global fixed-point grid (overlays cnt + ext)
+    unsigned long long* g64;   // kSmem64 / kGlobal64 / kSmemFix: global fixed-point grid (overlays cnt + ext)
+    int nb;                    // kSmemFix: bins per sign plane
 
     __device__ __forceinline__ void add_int(int bin, int delta) {
         if (MODE == kSmem32) {
@@ -83,7 +94,27 @@ struct Hist {
             atomicAdd(&g_cnt[bin], delta);
         }
     }
+    // kSmemFix: `d` units of 2^-24 onto the positive (neg == false) or negative plane of `bin`
+    __device__ __forceinline__ void add_fix(int bin, unsigned d, bool neg) {
+        unsigned* cell = reinterpret_cast<unsigned*>(s_i) + (neg ? nb : 0) + bin;
+        const unsigned old = atomicAdd(cell, d);
+        if (old + d < old)                              // this add wrapped the 32-bit bin: credit 2^32 units
+            atomicAdd(&g64[bin], neg ? (unsigned long long)(-(1ll << 32)) : (1ull << 32));
+    }
     __device__ __forceinline__ void add_float(int bin, float w) {
+        if (MODE == kSmemFix) {
+            const float mag = fabsf(w);
+            if (mag < 128.f) {
+                const unsigned d = __float2uint_rn(mag * (float)(1 << kFixBits));
+                unsigned* cell = reinterpret_cast<unsigned*>(s_i) + (w < 0.f ? nb : 0) + bin;
+                const unsigned old = atomicAdd(cell, d);
+                if (old + d < old)                      // this add wrapped the 32-bit bin: credit 2^32 units
+                    atomicAdd(&g64[bin], w < 0.f ? (unsigned long long)(-(1ll << 32)) : (1ull << 32));
+            } else {
+                atomicAdd(&g64[bin], (unsigned long long)__double2ll_rn((double)w * (double)(1 << kFixBits)));
+            }
+            return;
+        }
         if (MODE == kSmem64) atomicAdd(&s64[bin], to_fixed64(w));
         else if (MODE == kGlobal64) atomicAdd(&g64[bin], to_fixed64(w));
         else if (FLOAT_HIST && MODE == kSmem32) atomicAdd(&s_f[bin], w);
@@ -274,6 +305,40 @@ struct StackOp : Common {
     }
 };
 
+// One event through its encoder.  Voxels with >= 2 bins take the pair form (VoxelOp::pair: the event's two non-zero
+// weights fall on adjacent bins j, j + 1 -- same weights as run(), half the index / bounds arithmetic).
+template <class HT, class Op>
+__device__ __forceinline__ void event(HT& h, Op& op, long i, float x, float y, float t, float p) { op.run(h, i, x, y, t, p); }
+template <class HT>
+__device__ __forceinline__ void event(HT& h, VoxelOp& op, long i, float x, float y, float t, float p) {
+    if (op.bins < 2) { op.run(h, i, x, y, t, p); return; }
+    if (HT::kMode == kSmemFix) {
+        // Fast path of the common event -- in range, polarity +-1, 0 <= tn < bins - 1: with frac = tn - floor(tn) the
+        // reference's two weights max(0, 1 - |tn - b|) are exactly frac (bin j + 1) and 1 - frac (bin j) whenever
+        // tn >= 1 (differences of neighbouring floats are exact) and within 2^-25 of them for tn < 1, so both go out as
+        // integers: d_hi = round(frac * 2^24), d_lo = 2^24 - d_hi -- one conversion, no weight arithmetic in fp32.
+        Pix q = decode_xy(x, y, op.H, op.W, op.flip());
+        const float fb = (float)(op.bins - 1);
+        float tn;
+        if (op.flags & BMC_ENC_TNORM) tn = __fmul_rn(__fdiv_rn(__fsub_rn(t, op.t0), op.dt), fb);
+        else tn = __fmul_rn(t, fb);
+        const float fl = floorf(tn);
+        if (!q.oor && fabsf(p) == 1.f && tn >= 0.f && fl <= fb - 1.f) {
+            const unsigned dhi = __float2uint_rn(__fsub_rn(tn, fl) * (float)(1 << kFixBits));
+            const int slot = (int)fl * (op.H * op.W) + q.y * op.W + q.x;
+            const bool neg = p < 0.f;
+            if (dhi != (1u << kFixBits)) h.add_fix(slot, (1u << kFixBits) - dhi, neg);
+            if (dhi) h.add_fix(slot + op.H * op.W, dhi, neg);
+            return;
+        }
+    }
+    int slot; float lo, hi;
+    if (op.pair(i, x, y, t, p, slot, lo, hi)) {
+        if (lo != 0.f) h.add_float(slot, lo);
+        if (hi != 0.f) h.add_float(slot + op.H * op.W, hi);
+    }
+}
+
 // ---------------------------------------------------------------- the streaming kernel
 template <class Op, int MODE, int kThreads>
 __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nbins, int* g_cnt,
@@ -286,7 +351,8 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nb
     h.g_ext = g_ext;
     h.s64 = reinterpret_cast<unsigned long long*>(smem_raw);
     h.g64 = reinterpret_cast<unsigned long long*>(g_cnt);
-    const int words = (MODE == kSmem32) ? nbins : (MODE == kSmem16 ? (nbins + 1) / 2 : (MODE == kSmem64 ? 2 * nbins : 0));
+    h.nb = nbins;
+    const int words = (MODE == kSmem32) ? nbins : (MODE == kSmem16 ? (nbins + 1) / 2 : ((MODE == kSmem64 || MODE == kSmemFix) ? 2 * nbins : 0));
     for (int k = threadIdx.x; k < words; k += kThreads) h.s_i[k] = 0;
     if constexpr (Op::kBounds) {                 // bin ranges: 2*bins longs, read once per CTA
         __shared__ long s_bounds[128];
@@ -317,26 +383,32 @@ __global__ void __launch_bounds__(kThreads) scatter_kernel(Op op, long n, int nb
         const float4 p2 = two ? ldg_stream4(op.ps + i2) : z;
         const float4 t2 = (Op::kNeedT && two) ? ldg_stream4(op.ts + i2) : z;
         op.group(i, 4);
-        op.run(h, i + 0, x.x, y.x, t.x, p.x);
-        op.run(h, i + 1, x.y, y.y, t.y, p.y);
-        op.run(h, i + 2, x.z, y.z, t.z, p.z);
-        op.run(h, i + 3, x.w, y.w, t.w, p.w);
+        event(h, op, i + 0, x.x, y.x, t.x, p.x);
+        event(h, op, i + 1, x.y, y.y, t.y, p.y);
+        event(h, op, i + 2, x.z, y.z, t.z, p.z);
+        event(h, op, i + 3, x.w, y.w, t.w, p.w);
         if (two) {
             op.group(i2, 4);
-            op.run(h, i2 + 0, x2.x, y2.x, t2.x, p2.x);
-            op.run(h, i2 + 1, x2.y, y2.y, t2.y, p2.y);
-            op.run(h, i2 + 2, x2.z, y2.z, t2.z, p2.z);
-            op.run(h, i2 + 3, x2.w, y2.w, t2.w, p2.w);
+            event(h, op, i2 + 0, x2.x, y2.x, t2.x, p2.x);
+            event(h, op, i2 + 1, x2.y, y2.y, t2.y, p2.y);
+            event(h, op, i2 + 2, x2.z, y2.z, t2.z, p2.z);
+            event(h, op, i2 + 3, x2.w, y2.w, t2.w, p2.w);
         }
     }
     for (long i = (n4 << 2) + (long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
         op.group(i, 1);
-        op.run(h, i, op.xs[i], op.ys[i], Op::kNeedT ? op.ts[i] : 0.f, op.ps[i]);
+        event(h, op, i, op.xs[i], op.ys[i], Op::kNeedT ? op.ts[i] : 0.f, op.ps[i]);
     }
 
     if (MODE == kGlobal || MODE == kGlobal64) return;
     __syncthreads();
-    if (MODE == kSmem64) {
+    if (MODE == kSmemFix) {
+        const unsigned* su = reinterpret_cast<const unsigned*>(h.s_i);
+        for (int k = threadIdx.x; k < nbins; k += kThreads) {
+            const long long v = (long long)su[k] - (long long)su[nbins + k];
+            if (v) atomicAdd(&h.g64[k], (unsigned long long)v);
+        }
+    } else if (MODE == kSmem64) {
         for (int k = threadIdx.x; k < nbins; k += kThreads) {
             const unsigned long long v = h.s64[k];
             if (v) atomicAdd(&h.g64[k], v);
@@ -536,10 +608,10 @@ __global__ void finalize_kernel(const int* __restrict__ cnt, const float* __rest
 }
 
 // deterministic path: out = fp32(fixed-point sum * 2^-32), one rounding
-__global__ void finalize64_kernel(const long long* __restrict__ g64, float* __restrict__ out, long n) {
+__global__ void finalize64_kernel(const long long* __restrict__ g64, float* __restrict__ out, long n, double unit) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = (float)((double)g64[i] * (1.0 / 4294967296.0));
+    out[i] = (float)((double)g64[i] * unit);
 }
 
 // Bin boundaries of the stack encoders, evaluated exactly like encodings.py:172-178 + :75-97
@@ -741,7 +813,7 @@ int launch_threads(const Op& op, long n, int nbins, const Ws& w, int vec_ok, siz
 
 template <class Op, int MODE>
 int launch_mode(const Op& op, long n, int nbins, const Ws& w, int vec_ok, cudaStream_t st) {
-    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : (MODE == kSmem64 ? (size_t)nbins * 8 : 0));
+    size_t smem = MODE == kSmem32 ? (size_t)nbins * 4 : (MODE == kSmem16 ? (size_t)((nbins + 1) / 2) * 4 : ((MODE == kSmem64 || MODE == kSmemFix) ? (size_t)nbins * 8 : 0));
     int per_sm = 1;
     BMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, scatter_kernel<Op, MODE, kThreads>, kThreads, smem));
     // One 1024-thread CTA per SM keeps enough loads in flight (1024 x 2 groups x 3-4 arrays x 16 B >= 96 KB) and
@@ -770,7 +842,15 @@ int run_scatter(const Op& op, long n, long out_elems, float* out, void* ws, size
                 rc = out_elems <= kMaxBinsSmem64 ? launch_mode<Op, kSmem64>(op, n, nbins, w, vec_ok, st)
                                                  : launch_mode<Op, kGlobal64>(op, n, nbins, w, vec_ok, st);
                 if (rc) return rc;
-                finalize64_kernel<<<(unsigned)((out_elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(w.cnt), out, out_elems);
+                finalize64_kernel<<<(unsigned)((out_elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(w.cnt), out, out_elems, 1.0 / 4294967296.0);
+                BMC_CUDA(cudaGetLastError());
+                return BMC_OK;
+            }
+            if (out_elems <= kMaxBinsSmemFix) {
+                rc = launch_mode<Op, kSmemFix>(op, n, nbins, w, vec_ok, st);
+                if (rc) return rc;
+                finalize64_kernel<<<(unsigned)((out_elems + 255) / 256), 256, 0, st>>>(reinterpret_cast<const long long*>(w.cnt), out, out_elems,
+                                                                                      1.0 / (double)(1 << kFixBits));
                 BMC_CUDA(cudaGetLastError());
                 return BMC_OK;
             }
