@@ -378,7 +378,7 @@ def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
     import torch.distributed as dist
     import torch.nn.functional as F
     from bmcnet_esr_b200.models.BMCNet import BMCNet
-    from bmcnet_esr_b200.models._train import FusedAdamAMSGrad, allreduce_gradients
+    from bmcnet_esr_b200.models._train import FusedAdamAMSGrad, GraphedIteration, allreduce_gradients
     from oracle.make_golden import synth_counts
     dev, world, rank = cx.dev, cx.world, cx.rank
     sd, weights_desc = load_state('full')
@@ -404,31 +404,43 @@ def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
         if world > 1:
             n_red = allreduce_gradients(opt)
         opt.step()
-        return loss
+        return loss.detach()      # (a live autograd graph would keep the default stream's AccumulateGrad nodes alive)
 
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(n):
+            out = fn()
+        t1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / n, out
+
+    # (1) the iteration issued op by op from Python, as the reference's loop would run it on the drop-in module
     for _ in range(warm):
         iteration()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for _ in range(iters):
-        loss = iteration()
-    t1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t = torch.tensor([t0.elapsed_time(t1)], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item() / iters
+    ms_eager, loss = timed(iteration, iters)
+    # (2) the same iteration with zero_grad .. backward replayed as ONE CUDA graph (GraphedIteration): the product path
+    graphed = GraphedIteration(model, opt, xs, gts, warmup=1)
+    n_red = opt.grad.numel() if world > 1 else 0
+    graphed()
+    ms, loss = timed(graphed, max(iters, 5))
     finite = bool(torch.isfinite(loss))
-    del model, opt
+    del graphed, model, opt
     torch.cuda.empty_cache()
     return {'workload': 'BMCNet x4 training iteration (train.py:202-237): %d recurrent steps with BPTT, summed MSE, '
                         'Adam(amsgrad), NFS LR %dx%d, batch %d per GPU, data-parallel' % (seq_steps, h, w, batch),
             'weights': weights_desc, 'ms_per_iteration': ms, 'iterations_per_s': 1e3 / ms,
+            'ms_per_iteration_eager': ms_eager, 'how': 'zero_grad + forward + backward replayed as one CUDA graph, then the '
+            'all-reduce and the fused Adam launch (GraphedIteration); `ms_per_iteration_eager` = the same iteration issued '
+            'op by op from Python (host-bound)',
             'value': batch * seq_steps * world / (ms * 1e-3), 'unit': 'training frames/s (forward + backward + update)',
             'iterations': iters, 'batch_per_gpu': batch, 'sequence_steps': seq_steps, 'loss_finite': finite,
             'allreduce': {'elements': n_red, 'bytes': n_red * 4, 'collective': 'one NCCL all-reduce of the flat '

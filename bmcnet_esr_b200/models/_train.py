@@ -77,6 +77,7 @@ class _Ctx:
         self.loss_scale = float(loss_scale)
         self.wcache = {}
         self.cmaps = {}
+        self.gidx = {}
         self.ws = None
 
     def workspace(self, dev):
@@ -90,6 +91,17 @@ class _Ctx:
         if key not in self.cmaps:
             self.cmaps[key] = torch.tensor(idx, dtype=torch.int32, device=dev)
         return self.cmaps[key]
+
+    def gather_index(self, idx, dev):
+        """(clamped int64 index, fp32 0/1 mask [1,c,1,1]) of a channel list; cached, so that packing weights issues no
+        host-to-device copy (a CUDA-graph capture of the iteration, GraphedIteration, must not contain one)."""
+        key = (tuple(idx), str(dev))
+        hit = self.gidx.get(key)
+        if hit is None:
+            it = torch.tensor(idx, device=dev)
+            hit = (it.clamp(min=0), (it >= 0).view(1, -1, 1, 1).float())
+            self.gidx[key] = hit
+        return hit
 
     def packed_weight(self, weight, segs, mode, seg=None):
         """mode 'fwd': chunk-major forward weights for the K segments `segs` (lists of weight input channels, -1 =
@@ -106,14 +118,14 @@ class _Ctx:
         if mode == 'fwd':
             cols = []
             for idx in segs:
-                it = torch.tensor(idx, device=w.device)
-                ws = w.index_select(1, it.clamp(min=0)) * (it >= 0).view(1, -1, 1, 1)
+                it, mask = self.gather_index(idx, w.device)
+                ws = w.index_select(1, it) * mask
                 cols.append(ws.reshape(128, len(idx), kh * kw).permute(0, 2, 1).reshape(128, -1))     # [N, taps*c]
             wk = torch.cat(cols, 1)
         else:
             idx = segs[seg]
-            it = torch.tensor(idx, device=w.device)
-            ws = w.index_select(1, it.clamp(min=0)) * (it >= 0).view(1, -1, 1, 1)                      # [128 co, c, kh, kw]
+            it, mask = self.gather_index(idx, w.device)
+            ws = w.index_select(1, it) * mask                                                         # [128 co, c, kh, kw]
             wt = ws.permute(1, 0, 2, 3).flip(2, 3)                                                    # [c, 128 co, kh, kw] mirrored
             c = len(idx)
             if c < 128:
@@ -461,3 +473,85 @@ def allreduce_gradients(opt_or_params, group=None):
         g.copy_(flat[off:off + g.numel()].view_as(g))
         off += g.numel()
     return flat.numel()
+
+
+# ------------------------------------------------------------------------------------------ the iteration as a CUDA graph
+class GraphedIteration:
+    """One training iteration of the reference's loop (train.py:202-237: zero_grad, the sequence through the model with
+    the state carried, `loss += MSELoss`, `loss.backward()`, optional gradient all-reduce, Adam step) with everything
+    between `zero_grad` and the end of `backward` recorded ONCE as a CUDA graph and replayed afterwards.
+
+    Why: at the reference's batch (2 per GPU) the eager iteration is host-bound -- ~6,000 kernel-entry calls and ~20,000
+    small PyTorch ops per iteration through Python and the autograd engine, 450-480 ms for ~100 ms of GPU work.  Shapes
+    are static during training (fixed batch, sequence length and crop), so the launch sequence is too.
+
+    What is inside the graph: zeroing the flat gradient buffer, packing the fp16 weights from the CURRENT fp32
+    parameters (forward and mirrored/transposed dgrad packs, once per iteration), all forward / dgrad / wgrad kernels
+    and the PyTorch glue.  Outside: the NCCL all-reduce of the flat gradient buffer (world > 1) and the one-launch
+    fused Adam step (its bias corrections are host scalars that change every step).
+
+        it = GraphedIteration(model, opt, xs_example, gts_example)
+        loss = it(xs, gts)          # copies the inputs into the static buffers, replays, reduces, steps
+
+    `xs`: the sequence of model inputs [B,2,T,H,W] (any strides; `inp_cnt.transpose(1, 2)` in the reference), `gts`: the
+    targets [B,2,kH',kW'].  The returned loss is a 0-d tensor that the next call overwrites.
+
+    Build it before any eager iteration, or after the last eager loss tensor is gone: a live autograd graph of an eager
+    iteration keeps the parameters' AccumulateGrad nodes -- which remember the stream they were created on -- alive, and
+    the capture then fails with "dependency created on uncaptured work in another stream"."""
+
+    def __init__(self, model, opt, xs, gts, group=None, warmup=2, capture_error_mode='thread_local'):
+        if not isinstance(opt, FusedAdamAMSGrad):
+            raise _lib.BmcError('GraphedIteration needs FusedAdamAMSGrad (the gradients must live in one static buffer)')
+        self.model, self.opt, self.group = model, opt, group
+        dev = opt.flat.device
+        self.n_state = 3 if hasattr(model.neuro, 'conv_hs') else 1
+        self.xs = [x.to(dev).float().contiguous().clone() for x in xs]
+        self.gts = [g.to(dev).float().contiguous().clone() for g in gts]
+        self.loss = None
+        model.train()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                    # lazy module loads, kernel attributes, index caches: not capturable
+                self._body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        context(model).wcache.clear()                  # the packs must be rebuilt INSIDE the graph, from the live parameters
+        self.graph = torch.cuda.CUDAGraph()
+        # 'thread_local': a training process has other threads that touch CUDA (pinned-memory loaders, the clock sampler of
+        # bench.py); their calls are not part of this stream's capture and must not invalidate it
+        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+            self.loss = self._body()
+        context(model).wcache.clear()                  # (entries point into the graph's pool; never reuse them eagerly)
+
+    def _body(self):
+        m, dev = self.model, self.opt.flat.device
+        self.opt.zero_grad()
+        b, _, _, h, w = self.xs[0].shape
+        st = [torch.zeros(b, 128, h, w, device=dev) for _ in range(self.n_state)]
+        st.append(torch.zeros(b, 2 * m.scale * m.scale, h, w, device=dev))
+        loss, init = 0, True
+        for x, gt in zip(self.xs, self.gts):
+            st = list(m(x, *st, init))
+            init = False
+            pred = st[-1]
+            if pred.shape[-2:] != gt.shape[-2:]:       # train.py:224-228
+                pred = F.interpolate(pred, size=gt.shape[-2:], mode='bicubic', align_corners=False)
+            loss = loss + F.mse_loss(pred, gt)
+        loss.backward()
+        return loss.detach()
+
+    def __call__(self, xs=None, gts=None):
+        if xs is not None:
+            for dst, src in zip(self.xs, xs):
+                dst.copy_(src, non_blocking=True)
+        if gts is not None:
+            for dst, src in zip(self.gts, gts):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                      and torch.distributed.get_world_size() > 1):
+            allreduce_gradients(self.opt, self.group)
+        self.opt.step()
+        return self.loss
