@@ -36,6 +36,8 @@ struct alignas(64) WgradParams {
     int rows;                                    // B * R (multiple of 128)
     int n_split, rows_per_split;                 // rows_per_split: multiple of 64
     float* partial;                              // [split][tap][128][x_ch]
+    const act_t* dy_ptr;                         // bias gradient (optional): column sums of dY, one partial row per split,
+    float* bias_partial;                         // [split][128] -- summed by the idle epilogue warps of the tap-0 CTAs
 };
 
 template <int XCH>
@@ -107,6 +109,16 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc(const __grid_constant__ W
         const int q = warp & 3;
         const int row = q * 32 + lane;             // output channel co
         float* dst = p.partial + (((long)split * p.n_taps + tap) * 128 + row) * XCH;
+        if (p.bias_partial && tap == 0) {          // dbias partial of this pixel split, while the MMAs run
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+            const act_t* d = p.dy_ptr + (long)r0 * 128 + row;
+            int r = r0;
+            for (; r + 4 <= r1; r += 4, d += 4 * 128) {
+                s0 += from_act(d[0]); s1 += from_act(d[128]); s2 += from_act(d[256]); s3 += from_act(d[384]);
+            }
+            for (; r < r1; ++r, d += 128) s0 += from_act(d[0]);
+            p.bias_partial[split * 128 + row] = (s0 + s1) + (s2 + s3);
+        }
         if (iters > 0) {
             mbar_wait(&acc_bar, 0);
             tc_fence_after_sync();
@@ -137,11 +149,21 @@ __global__ void __launch_bounds__(kWgThreads) wgrad_tc(const __grid_constant__ W
 }
 
 // grad[(co * cin_total + cmap[ci]) * taps + tap] += scale * sum_split partial[split][tap][co][ci]
+// (+ the last block, when `bias_partial` is given: grad_b[co] += scale * sum_split bias_partial[split][co])
 __global__ void wgrad_reduce(const float* __restrict__ partial, int n_split, int taps, int x_ch,
                              const int* __restrict__ cmap, int cin_total, int n_out, float scale,
-                             float* __restrict__ grad) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+                             float* __restrict__ grad, const float* __restrict__ bias_partial, float* __restrict__ grad_b) {
     const int per_split = taps * 128 * x_ch;
+    if (bias_partial && blockIdx.x == gridDim.x - 1) {
+        const int c = threadIdx.x;
+        if (c < n_out) {
+            float s = 0.f;
+            for (int k = 0; k < n_split; ++k) s += bias_partial[k * 128 + c];
+            grad_b[c] += scale * s;
+        }
+        return;
+    }
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= per_split) return;
     const int ci = idx % x_ch;
     const int co = (idx / x_ch) % 128;
@@ -151,24 +173,6 @@ __global__ void wgrad_reduce(const float* __restrict__ partial, int n_split, int
     float s = 0.f;
     for (int k = 0; k < n_split; ++k) s += partial[(long)k * per_split + idx];      // fixed order: deterministic
     grad[((long)co * cin_total + dst_c) * taps + tap] += scale * s;
-}
-
-// dbias[co] += scale * sum_rows dY[row][co]: one CTA per 32 channels x row slice, fixed-order two-stage sum
-__global__ void bias_grad_partial(const act_t* __restrict__ dy, long rows, int rows_per_cta, float* __restrict__ partial) {
-    // blockDim = (128 channels); grid.x = row slices
-    const int c = threadIdx.x;
-    const long r0 = (long)blockIdx.x * rows_per_cta;
-    const long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
-    float s = 0.f;
-    for (long r = r0; r < r1; ++r) s += from_act(dy[r * 128 + c]);
-    partial[(long)blockIdx.x * 128 + c] = s;
-}
-__global__ void bias_grad_reduce(const float* __restrict__ partial, int n, int n_out, float scale, float* __restrict__ grad) {
-    const int c = threadIdx.x;
-    if (c >= n_out) return;
-    float s = 0.f;
-    for (int k = 0; k < n; ++k) s += partial[(long)k * 128 + c];
-    grad[c] += scale * s;
 }
 
 // dx = dy * (y > 0), elementwise on act16 pairs (ReLU backward; F.relu at BMCNet.py:64-73, submodules.py:33)
@@ -235,9 +239,14 @@ __global__ void __launch_bounds__(kLnbThreads) layernorm_backward(const act_t* _
 }
 __global__ void layernorm_backward_reduce(const float* __restrict__ partial, int n, float scale, float* __restrict__ dgamma,
                                           float* __restrict__ dbeta) {
-    const int c = threadIdx.x;                   // 256 threads: 0..127 gamma, 128..255 beta
+    __shared__ float s_part[4][256];             // 1024 threads: 4 interleaved partial sums per column, fixed order
+    const int c = threadIdx.x & 255, part = threadIdx.x >> 8;      // columns 0..127 gamma, 128..255 beta
     float s = 0.f;
-    for (int k = 0; k < n; ++k) s += partial[(long)k * 256 + c];
+    for (int k = part; k < n; k += 4) s += partial[(long)k * 256 + c];
+    s_part[part][c] = s;
+    __syncthreads();
+    if (part) return;
+    s = (s_part[0][c] + s_part[1][c]) + (s_part[2][c] + s_part[3][c]);
     if (c < 128) dgamma[c] += scale * s; else dbeta[c - 128] += scale * s;
 }
 
@@ -292,6 +301,9 @@ extern "C" BMC_EXPORT int bmc_conv_wgrad(const void* dy_act16, const void* x_act
     p.rows_per_split = (chunks + n_split - 1) / n_split * 64;
     p.n_split = n_split;
     p.partial = static_cast<float*>(workspace);
+    const int per_split = taps * 128 * x_ch;
+    p.dy_ptr = static_cast<const act_t*>(dy_act16);
+    p.bias_partial = grad_b ? p.partial + (size_t)n_split * per_split : nullptr;
     const int smem = kWgStages * (2 + p.x_chunks) * kWgBox + 1024;
     static PerDevice configured_dev;
     int& configured = configured_dev.cur();
@@ -304,17 +316,9 @@ extern "C" BMC_EXPORT int bmc_conv_wgrad(const void* dy_act16, const void* x_act
     if (x_ch == 128) wgrad_tc<128><<<grid, kWgThreads, smem, st>>>(p);
     else wgrad_tc<64><<<grid, kWgThreads, smem, st>>>(p);
     BMC_CUDA(cudaGetLastError());
-    const int per_split = taps * 128 * x_ch;
-    wgrad_reduce<<<(per_split + 255) / 256, 256, 0, st>>>(p.partial, n_split, taps, x_ch, cmap, cin_total, n_out, scale, grad_w);
+    wgrad_reduce<<<(per_split + 255) / 256 + (grad_b ? 1 : 0), 256, 0, st>>>(p.partial, n_split, taps, x_ch, cmap, cin_total, n_out,
+                                                                             scale, grad_w, p.bias_partial, grad_b);
     BMC_CUDA(cudaGetLastError());
-    if (grad_b) {
-        float* bpart = p.partial + (size_t)n_split * per_split;
-        const int slices = 256;
-        const int rows_per = (int)((g.rows() + slices - 1) / slices);
-        bias_grad_partial<<<slices, 128, 0, st>>>(static_cast<const act_t*>(dy_act16), g.rows(), rows_per, bpart);
-        bias_grad_reduce<<<1, 128, 0, st>>>(bpart, slices, n_out, scale, grad_b);
-        BMC_CUDA(cudaGetLastError());
-    }
     return BMC_OK;
 }
 
@@ -358,7 +362,7 @@ extern "C" BMC_EXPORT int bmc_layernorm_rows_backward(const void* x_act16, const
     float* partial = static_cast<float*>(workspace);
     layernorm_backward<<<grid, kLnbThreads, 0, st>>>(static_cast<const act_t*>(x_act16), static_cast<const act_t*>(dy_act16), gamma,
                                                      eps, (long)rows, static_cast<act_t*>(dx_act16), partial);
-    layernorm_backward_reduce<<<1, 256, 0, st>>>(partial, grid, scale, grad_gamma, grad_beta);
+    layernorm_backward_reduce<<<1, 1024, 0, st>>>(partial, grid, scale, grad_gamma, grad_beta);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
 }

@@ -79,12 +79,19 @@ class _Ctx:
         self.cmaps = {}
         self.gidx = {}
         self.ws = None
+        self.ln_ws = None
+        self.side = None          # GraphedIteration: the stream the weight-gradient kernels are recorded on
 
     def workspace(self, dev):
         nbytes = lib().bmc_conv_wgrad_workspace_bytes(WGRAD_SPLITS, 9, 128)
         if self.ws is None or self.ws.device != dev:
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         return self.ws
+
+    def ln_workspace(self, dev):
+        if self.ln_ws is None or self.ln_ws.device != dev:
+            self.ln_ws = torch.empty(lib().bmc_layernorm_rows_backward_workspace_bytes(), dtype=torch.uint8, device=dev)
+        return self.ln_ws
 
     def cmap(self, idx, dev):
         key = (tuple(idx), str(dev))
@@ -178,9 +185,23 @@ class _ConvFn(torch.autograd.Function):
         gw = _grad_buf(conv.weight)
         gb = _grad_buf(conv.bias)
         inv = 1.0 / tc.loss_scale
-        for i, (src, idx) in enumerate(zip(srcs, segs)):
-            K.conv_wgrad(dz, src, taps, b, h, w, tc.cmap(idx, dev), conv.in_channels, conv.out_channels, inv,
-                         gw, gb if (i == 0 and ctx.use_bias) else None, ws, WGRAD_SPLITS)
+
+        def wgrads():
+            for i, (src, idx) in enumerate(zip(srcs, segs)):
+                K.conv_wgrad(dz, src, taps, b, h, w, tc.cmap(idx, dev), conv.in_channels, conv.out_channels, inv,
+                             gw, gb if (i == 0 and ctx.use_bias) else None, ws, WGRAD_SPLITS)
+
+        if tc.side is None:
+            wgrads()
+        else:
+            # Nothing downstream in the backward pass reads a weight gradient, so inside a captured iteration the wgrad
+            # kernels go to ONE side stream (they stay ordered among themselves: shared workspace, aliased gradient
+            # buffers) and overlap the dgrad chain, which at training batches fills a fifth of the SMs.
+            tc.side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(tc.side):
+                wgrads()
+            for t in (dz, *srcs):
+                t.record_stream(tc.side)
         grads = []
         for i, src in enumerate(srcs):
             if not ctx.needs_input_grad[7 + i]:
@@ -234,8 +255,51 @@ class _LayerNormFn(torch.autograd.Function):
         (x,) = ctx.saved_tensors
         tc, norm = ctx.tc, ctx.norm
         dx = K.layernorm_rows_backward(x, dy.contiguous(), norm.weight.detach(), norm.eps, 1.0 / tc.loss_scale,
-                                       _grad_buf(norm.weight), _grad_buf(norm.bias), tc.workspace(x.device))
+                                       _grad_buf(norm.weight), _grad_buf(norm.bias), tc.ln_workspace(x.device))
         return dx, None, None, None
+
+
+class _tf32_matmul:
+    """The attention products run on the tensor cores as TF32 x TF32 -> fp32 (cuBLAS).  Their big operands (centres, v,
+    incoming gradients) hold 16-bit values, which TF32 represents exactly, so those products are exact; fp32 operands
+    (softmax probabilities, logit gradients) are rounded to 11 bits like every other activation of this path.  The
+    default fp32 path of torch.bmm is a SIMT sgemm: 76 us per call at batch 2, a fifth of the whole iteration."""
+
+    def __enter__(self):
+        self.prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+
+    def __exit__(self, *exc):
+        torch.backends.cuda.matmul.allow_tf32 = self.prev
+
+
+class _AttendFn(torch.autograd.Function):
+    """out = (softmax(centres^T v * scale) v^T)^T per image (BIE.forward, submodules.py:69-73) on packed rows
+    c, v: act16 [B*R, 128] (halo rows are zero and contribute nothing).  Logits and probabilities stay fp32 (the logits
+    reach +-33: 16-bit logits would cost 3 % in the softmax)."""
+
+    @staticmethod
+    def forward(ctx, c, v, b, r, scale):
+        cf, vf = c.view(b, r, 128).float(), v.view(b, r, 128).float()
+        with _tf32_matmul():
+            att = torch.bmm(cf.transpose(1, 2), vf)                        # [b, c, c'] = centres . v^T (:69-70)
+            p = torch.softmax(att * scale, -1)
+            out = torch.bmm(vf, p.transpose(1, 2))                         # (P v)^T in row layout (:72-73)
+        ctx.save_for_backward(c, v, p)
+        ctx.geom, ctx.scale = (b, r), scale
+        return out.reshape(b * r, 128).to(c.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        c, v, p = ctx.saved_tensors
+        (b, r), scale = ctx.geom, ctx.scale
+        cf, vf, gf = c.view(b, r, 128).float(), v.view(b, r, 128).float(), g.reshape(b, r, 128).float()
+        with _tf32_matmul():
+            dp = torch.bmm(gf.transpose(1, 2), vf)                         # out[r,c] = sum_c' v[r,c'] p[c,c']
+            datt = p * (dp - (dp * p).sum(-1, keepdim=True)) * scale       # softmax backward, then the logit scale
+            dv = torch.baddbmm(torch.bmm(gf, p), cf, datt)                 # through `out` and through the logits
+            dc = torch.bmm(vf, datt.transpose(1, 2))
+        return dc.reshape(b * r, 128).to(c.dtype), dv.reshape(b * r, 128).to(v.dtype), None, None, None
 
 
 def layernorm_rows(tc, norm, y):
@@ -259,10 +323,7 @@ def bie(tc, m, x1, x2, xs, geom):
     v2 = conv(tc, m.v2, [x2], [_R128], geom)
 
     def attend(c, v):
-        cf, vf = c.view(b, r, 128).float(), v.view(b, r, 128).float()
-        att = torch.bmm(cf.transpose(1, 2), vf) * m.scale                 # [b, c, c'] = centres . v^T (:69-70)
-        p = torch.softmax(att, -1)
-        return torch.bmm(vf, p.transpose(1, 2)).reshape(b * r, 128).to(c.dtype)     # (P v)^T in row layout (:72-73)
+        return _AttendFn.apply(c, v, b, r, float(m.scale))
 
     o1, o2 = attend(c1, v1), attend(c2, v2)
     ns = conv(tc, m.unclustering, [c1, c2], two, geom) + xs
@@ -500,7 +561,7 @@ class GraphedIteration:
     iteration keeps the parameters' AccumulateGrad nodes -- which remember the stream they were created on -- alive, and
     the capture then fails with "dependency created on uncaptured work in another stream"."""
 
-    def __init__(self, model, opt, xs, gts, group=None, warmup=2, capture_error_mode='thread_local'):
+    def __init__(self, model, opt, xs, gts, group=None, warmup=2, capture_error_mode='thread_local', wgrad_stream=True):
         if not isinstance(opt, FusedAdamAMSGrad):
             raise _lib.BmcError('GraphedIteration needs FusedAdamAMSGrad (the gradients must live in one static buffer)')
         self.model, self.opt, self.group = model, opt, group
@@ -518,12 +579,17 @@ class GraphedIteration:
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         context(model).wcache.clear()                  # the packs must be rebuilt INSIDE the graph, from the live parameters
+        tc = context(model)
+        tc.side = torch.cuda.Stream(device=dev) if wgrad_stream else None
         self.graph = torch.cuda.CUDAGraph()
         # 'thread_local': a training process has other threads that touch CUDA (pinned-memory loaders, the clock sampler of
         # bench.py); their calls are not part of this stream's capture and must not invalidate it
         with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
             self.loss = self._body()
-        context(model).wcache.clear()                  # (entries point into the graph's pool; never reuse them eagerly)
+            if tc.side is not None:
+                torch.cuda.current_stream(dev).wait_stream(tc.side)      # join: the gradients are complete when the graph is
+        tc.side = None
+        tc.wcache.clear()                              # (entries point into the graph's pool; never reuse them eagerly)
 
     def _body(self):
         m, dev = self.model, self.opt.flat.device
