@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('BMC_B200_LIB') or os.path.join(_HERE, 'libbmc_b200.so')
 
 ENC_FLIP_Y, ENC_MUTATE, ENC_NO_QUIRKS, ENC_TNORM, ENC_BILINEAR, ENC_SKIP_ZERO_ENDS, ENC_DETERMINISTIC = 0x1, 0x2, 0x4, 0x8, 0x10, 0x20, 0x40
+ENC_SPLIT_BINS = 0x80
 MODEL_BMCNET, MODEL_BMCNET_PLAIN = 0, 1
 
 _vp, _i, _i64, _f, _sz, _u = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_size_t, C.c_uint

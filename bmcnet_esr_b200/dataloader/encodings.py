@@ -59,7 +59,14 @@ class deterministic:
 
 
 def _det():
-    return _lib.ENC_DETERMINISTIC if DETERMINISTIC else 0
+    return (_lib.ENC_DETERMINISTIC if DETERMINISTIC else 0) | (_lib.ENC_SPLIT_BINS if SPLIT_BINS else 0)
+
+
+# Grids beyond one SM's shared memory (events_to_channels from 2 x 58,112 pixels up, events_to_voxel* from 29,056 bins
+# up to 180x320 pixels) switch to the split-bins kernel at 2^24 events (csrc/encode.cu, role_kernel: a few CTAs stream
+# the same events, each holding a share of the bins); SPLIT_BINS = True takes it at any event count
+# (BMC_ENC_SPLIT_BINS) -- same results, used by the parity tests.
+SPLIT_BINS = False
 
 
 def _chk(*ts):
@@ -121,7 +128,8 @@ def events_to_channels(xs, ys, ps, sensor_size=(180, 240)):
     n = _chk(xs, ys, ps)
     h, w = sensor_size
     out = torch.empty(2, h, w, dtype=torch.float32, device=xs.device)
-    return _run(lambda *a: lib().bmc_encode_channels(_p(xs), _p(ys), _p(ps), n, h, w, *a, _MUT, stream_ptr()), out)
+    flags = _MUT | (_lib.ENC_SPLIT_BINS if SPLIT_BINS else 0)
+    return _run(lambda *a: lib().bmc_encode_channels(_p(xs), _p(ys), _p(ps), n, h, w, *a, flags, stream_ptr()), out)
 
 
 def events_to_channels_windows(xs, ys, ps, offsets, sensor_size=(180, 240)):

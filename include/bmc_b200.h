@@ -60,6 +60,10 @@ const char* bmc_act_dtype(void);
 #define BMC_ENC_DETERMINISTIC 0x40u /* image / voxel: accumulate the float weights as 64-bit fixed point (2^-32 units) so the
                                       result is bit-identical from run to run (integer sums do not depend on the order the
                                       atomics land in); |weight| < 2^30 per event.  Count encodings are always deterministic. */
+#define BMC_ENC_SPLIT_BINS 0x80u  /* channels / voxel on grids beyond one SM's shared memory: take the split-bins kernel
+                                    * (role_kernel, encode.cu: a few CTAs stream the same events, each holding a share of
+                                    * the bins) whatever the event count; by default it is used from 2^24 events up (below
+                                    * that the global-atomic path is as fast).  Same results. */
 
 /* Scratch bytes needed by any encoder call below for an output of `out_elems` floats. */
 size_t bmc_encode_workspace_bytes(int64_t out_elems);

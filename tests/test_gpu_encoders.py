@@ -303,3 +303,115 @@ def test_deterministic_image_paths(G):
     run(G.events_to_image)
     run(G.events_to_image_torch)
     run(G.events_to_image_torch, interpolation='bilinear')
+
+
+# ---------------------------------------------------------------------------------------------- bins split over CTAs (role_kernel)
+class _cluster_bins:
+    def __init__(self, G, on=True):
+        self.G, self.on = G, on
+
+    def __enter__(self):
+        self.prev, self.G.SPLIT_BINS = self.G.SPLIT_BINS, self.on
+
+    def __exit__(self, *exc):
+        self.G.SPLIT_BINS = self.prev
+
+
+@pytest.mark.parametrize('n,h,w,B,sort_t', [(300_017, 180, 320, 5, True), (450_000, 180, 320, 3, False), (250_001, 360, 640, 2, True),
+                                            (5, 360, 640, 2, True), (120_000, 120, 300, 9, True), (400_003, 360, 640, 3, True)])
+def test_cluster_bins_against_oracle(G, n, h, w, B, sort_t):
+    """role_kernel (a few CTAs stream the same events, each holding a share of the bins in shared memory) forced at small
+    event counts: events_to_channels bit-exact incl. the F9 leak and the (deferred) in-place zeroing, events_to_voxel /
+    events_to_voxel_torch within the 1e-6 bar -- on time-sorted input (the fast path) and on shuffled timestamps (most
+    events take the global-atomic path)."""
+    ev = list(synth_events(n, h, w, seed=n % 89, oor=0.04, dup=True, frac=True))
+    if not sort_t:
+        ev[2] = np.random.default_rng(3).permutation(ev[2])
+    cases = {'channels': EXACT['channels'], 'voxel': FLOAT['voxel'], 'voxel_torch': FLOAT['voxel_torch']}
+    for name, fn in cases.items():
+        if name == 'voxel_torch' and not sort_t:
+            continue                                  # the reference's ts[0] / ts[-1] normalisation assumes sorted stamps
+        ca, ga = [x.copy() for x in ev], _gpu(ev)
+        ref = fn(E, ca, h, w, B)
+        with _cluster_bins(G):
+            got = fn(G, ga, h, w, B).cpu().numpy()
+        assert got.shape == ref.shape, name
+        if name == 'channels':
+            assert np.array_equal(got, ref), (name, float(np.abs(got - ref).max()))
+        else:
+            ok, err, tol = _float_close(got, ref, ev, h, w)
+            assert ok, (name, err, tol)
+        for c, gt in zip(ca, ga):
+            assert np.array_equal(c, gt.cpu().numpy()), name
+
+
+def test_cluster_bins_skewed_and_heavy_pixels(G):
+    """Adversarial streams: (1) every event on ONE pixel -- the 16-bit counters / 32-bit fixed-point sums carry many
+    times; (2) all events in one role's share of the pixels; (3) more out-of-range events than the deferred-zeroing list
+    holds.  Counts stay bit-exact against bincount, voxels are bit-reproducible and match a float64 sum."""
+    h, w, n = 360, 640, 3_000_000
+    dev = 'cuda'
+    g = torch.Generator(device=dev).manual_seed(11)
+    ps = (torch.randint(0, 2, (n,), device=dev, generator=g) * 2 - 1).float()
+    for mode in ('one_pixel', 'one_tile'):
+        if mode == 'one_pixel':
+            xs, ys = torch.full((n,), 17.0, device=dev), torch.full((n,), 300.0, device=dev)
+        else:
+            xs = torch.randint(0, w, (n,), device=dev, generator=g).float()
+            ys = torch.randint(0, 40, (n,), device=dev, generator=g).float()
+        with _cluster_bins(G):
+            got = G.events_to_channels(xs.clone(), ys.clone(), ps.clone(), sensor_size=(h, w))
+        pix = ((h - 1 - ys.long()) * w + xs.long()) + (ps < 0).long() * h * w
+        ref = torch.bincount(pix, minlength=2 * h * w).view(2, h, w).float()
+        assert torch.equal(got, ref), mode
+    # (3) 200k out-of-range events (> 65536 list entries): the zeroing falls back to a scan; F9 leak at [1, H-1, 0]
+    xs = torch.randint(0, w, (n,), device=dev, generator=g).float()
+    ys = torch.randint(0, h, (n,), device=dev, generator=g).float()
+    xs[:200_000] = float(w) + 3.0
+    xc, yc = xs.clone(), ys.clone()
+    with _cluster_bins(G):
+        got = G.events_to_channels(xc, yc, ps, sensor_size=(h, w))
+    inr = xs < w
+    pix = ((h - 1 - ys[inr].long()) * w + xs[inr].long()) + (ps[inr] < 0).long() * h * w
+    ref = torch.bincount(pix, minlength=2 * h * w).view(2, h, w).float()
+    ref[1, h - 1, 0] += float((ps[:200_000] < 0).sum())
+    assert torch.equal(got, ref)
+    assert float(xc[:200_000].abs().sum()) == 0.0 and float(yc[:200_000].abs().sum()) == 0.0 and torch.equal(xc[200_000:], xs[200_000:])
+    # voxels, 180x320: the forced split-bins path across two runs and against a float64 sum
+    h, w, B = 180, 320, 5
+    ts = torch.sort(torch.rand(n, device=dev, generator=g))[0]
+    xs, ys = torch.full((n,), 5.0, device=dev), torch.full((n,), 7.0, device=dev)
+    with _cluster_bins(G):
+        a = G.events_to_voxel(xs.clone(), ys.clone(), ts, ps, B, sensor_size=(h, w))
+        b = G.events_to_voxel(xs.clone(), ys.clone(), ts, ps, B, sensor_size=(h, w))
+    assert torch.equal(a, b)                                       # integer sums: bit-reproducible
+    tn = ts.double() * (B - 1)
+    ref = torch.zeros(B, dtype=torch.float64, device=dev)
+    for k in range(B):
+        ref[k] = (ps.double() * (1 - (tn - k).abs()).clamp(min=0)).sum()
+    got = a[:, h - 1 - 7, 5].double()
+    assert float((got - ref).abs().max()) <= 2.0 ** -24 * n * 0.5 + 1e-3, (got, ref)
+    assert float(a.abs().sum() - a[:, h - 1 - 7, 5].abs().sum()) == 0.0
+
+
+def test_cluster_bins_full_size(G):
+    """2^26 events (the default dispatch: no flag): 360x640 counts bit-exact against bincount; 180x320 voxels: total
+    mass, and equality with the sum of the two halves of the stream encoded separately to 1e-6."""
+    n, dev = 1 << 26, 'cuda'
+    g = torch.Generator(device=dev).manual_seed(5)
+    h, w = 360, 640
+    xs = torch.randint(0, w, (n,), device=dev, generator=g).float()
+    ys = torch.randint(0, h, (n,), device=dev, generator=g).float()
+    ps = (torch.randint(0, 2, (n,), device=dev, generator=g) * 2 - 1).float()
+    got = G.events_to_channels(xs, ys, ps, sensor_size=(h, w))
+    pix = ((h - 1 - ys.long()) * w + xs.long()) + (ps < 0).long() * h * w
+    assert torch.equal(got, torch.bincount(pix, minlength=2 * h * w).view(2, h, w).float())
+    del got, pix
+    h, w, B = 180, 320, 5
+    xs, ys = (xs * 0.5).floor(), (ys * 0.5).floor()
+    ts = torch.sort(torch.rand(n, device=dev, generator=g))[0]
+    full = G.events_to_voxel(xs, ys, ts, ps, B, sensor_size=(h, w))
+    assert abs(float(full.double().sum()) - float(ps.double().sum())) <= 1e-6 * n
+    half = n // 2
+    parts = sum(G.events_to_voxel(xs[s], ys[s], ts[s], ps[s], B, sensor_size=(h, w)) for s in (slice(0, half), slice(half, n)))
+    assert float((full - parts).abs().max()) <= 1e-6 * max(1.0, float(full.abs().max())) * 4
