@@ -330,7 +330,8 @@ def run_workload(cx, name, batch, Ksteps, Wsteps, sustained=True):
         cnt = G.events_to_channels_windows(d[0], d[1], d[2], offsets, sensor_size=(h, w))
         ev_used[k & 1].record(main_s)
         x = cnt.view(B, 2, 2, h, w).transpose(1, 2)
-        st = list(model(x, *st, init))                                               # the reference-facing call
+        with torch.no_grad():                                                        # infer_BMCNet.py:144 (@torch.no_grad())
+            st = list(model(x, *st, init))                                           # the reference-facing call
         done = torch.cuda.Event()
         done.record(main_s)
         with torch.cuda.stream(copy_s):
