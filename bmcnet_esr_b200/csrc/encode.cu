@@ -652,18 +652,21 @@ struct VoxelRole {
         return (tn >= 0.f && fl <= (float)(op.bins - 2)) ? (int)fl : -1;
     }
     __device__ __forceinline__ int slot_of(long i) const { return slot_from(op.ts[i]); }
-    __device__ __forceinline__ void event(unsigned* bins, int role, int cur, long i, float x, float y, float t, float p) const {
-        Pix q = decode_xy(x, y, op.H, op.W, op.flip());
-        const float tn = tnorm(t), fl = floorf(tn);
-        if (!q.oor && fabsf(p) == 1.f && tn >= 0.f && fl == (float)cur) {
-            const int pix = q.y * op.W + q.x, plane = op.H * op.W;
-            const long gi = (long)cur * plane + pix;
+    // ROLE and TN (BMC_ENC_TNORM) are compile-time: the common event is ~40 instructions, one shared-memory atomic
+    template <int ROLE, bool TN>
+    __device__ __forceinline__ void event(unsigned* bins, int cur, float fcur, float fb, long i, float x, float y, float t, float p) const {
+        const float tn = TN ? __fmul_rn(__fdiv_rn(__fsub_rn(t, op.t0), op.dt), fb) : __fmul_rn(t, fb);
+        const float fl = floorf(tn);
+        const bool in = (x < (float)op.W) & (x >= 0.f) & (y < (float)op.H) & (y >= 0.f);
+        if (in & (fabsf(p) == 1.f) & (fl == fcur)) {                // (fl == fcur >= 0 implies tn >= 0)
+            const int yy = (int)y, pix = (op.flip() ? op.H - 1 - yy : yy) * op.W + (int)x;
             const bool neg = p < 0.f;
-            if (role == 0) {
+            if (ROLE == 0) {
                 const unsigned dhi = __float2uint_rn(__fsub_rn(tn, fl) * (float)(1 << kFixBits));
                 const unsigned d = neg ? (1u << kFixBits) - dhi : dhi;
                 const unsigned old = atomicAdd(&bins[pix], d);
                 if (old + d < old) {                 // U wrapped: 2^32 units move from bin j to bin j + 1
+                    const long plane = (long)op.H * op.W, gi = (long)cur * plane + pix;
                     atomicAdd(&g64[gi], (unsigned long long)(-(1ll << 32)));
                     atomicAdd(&g64[gi + plane], 1ull << 32);
                 }
@@ -671,6 +674,7 @@ struct VoxelRole {
                 const int sh = neg ? 16 : 0;
                 const unsigned old = atomicAdd(&bins[pix], 1u << sh);
                 if (((old >> sh) & 0xFFFFu) == 0x7FFFu) {      // 16-bit count at 0x8000: take 32768 events out (Hist::add_int)
+                    const long plane = (long)op.H * op.W, gi = (long)cur * plane + pix;
                     atomicSub(&bins[pix], 0x8000u << sh);
                     if (neg) atomicAdd(&g64[gi + plane], (unsigned long long)(-(1ll << (15 + kFixBits))));
                     else atomicAdd(&g64[gi], 1ull << (15 + kFixBits));
@@ -678,8 +682,8 @@ struct VoxelRole {
             }
             return;
         }
-        if (role != 0) return;
-        if (q.oor && mutate) oor.add(i);
+        if (ROLE != 0) return;
+        if (!in && mutate) oor.add(i);
         int slot; float lo, hi;
         if (op.pair(i, x, y, t, p, slot, lo, hi)) {
             if (lo != 0.f) atomicAdd(&g64[slot], (unsigned long long)__double2ll_rn((double)lo * (double)(1 << kFixBits)));
@@ -704,32 +708,28 @@ struct VoxelRole {
     }
 };
 
-template <class R>
-__global__ void __launch_bounds__(kRoleThreads, 1) role_kernel(R pol, long n, int roles, int vec_ok) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    unsigned* bins = reinterpret_cast<unsigned*>(smem_raw);
+template <class R, int ROLE, bool TN>
+__device__ __forceinline__ void role_body(R& pol, unsigned* bins, long n, int grp, int G, int vec_ok) {
     const int tid = threadIdx.x;
-    const int role = blockIdx.x % roles, grp = blockIdx.x / roles, G = gridDim.x / roles;
-    for (int k = tid; k < pol.words(); k += kRoleThreads) bins[k] = 0u;
-    pol.op.prepare(n);
-    __syncthreads();
+    const float fb = (float)(pol.op.bins - 1);
     int cur = -2;                                   // no slot yet
-    // the events of this group: whole 4-event blocks [b_lo, b_hi) (vector loads) or single events when unaligned
+    float fcur = __int_as_float(0x7fc00000);
+    // the events of this group: whole 4-event blocks (vector loads) or single events when unaligned
     const long units = vec_ok ? (n >> 2) : n;
     const long per = (units + G - 1) / G;
     const long u_lo = (long)grp * per, u_hi = min(units, u_lo + per);
     const int w = vec_ok ? 4 : 1;
     // Two units per thread and iteration, all loads issued before the first atomic; the time stamp that decides the NEXT
     // iteration's slot is requested now and looked at after this iteration's events (no dependent load on the path).
-    float t_first = (R::kNeedT && u_lo < u_hi) ? pol.op.ts[u_lo * w] : 0.f;
+    float t_first = u_lo < u_hi ? pol.op.ts[u_lo * w] : 0.f;
     for (long base = u_lo; base < u_hi; base += 2 * kRoleThreads) {
         const int slot = pol.slot_from(t_first);     // uniform: the iteration's first event
         const long nb = base + 2 * kRoleThreads;
-        if (R::kNeedT && nb < u_hi) t_first = ldg_stream1(pol.op.ts + nb * w);
+        if (nb < u_hi) t_first = ldg_stream1(pol.op.ts + nb * w);
         if (slot != cur) {
             __syncthreads();
-            if (cur >= 0) pol.flush(bins, role, cur);
-            cur = slot;
+            if (cur >= 0) pol.flush(bins, ROLE, cur);
+            cur = slot; fcur = slot >= 0 ? (float)slot : __int_as_float(0x7fc00000);      // NaN: no event matches
             __syncthreads();
         }
         const long u = base + tid, u2 = u + kRoleThreads;
@@ -738,36 +738,49 @@ __global__ void __launch_bounds__(kRoleThreads, 1) role_kernel(R pol, long n, in
             const bool one = u < u_hi, two = u2 < u_hi;
             const long i = u << 2, i2 = u2 << 2;
             const float4 x = one ? ldg_stream4(pol.op.xs + i) : z, y = one ? ldg_stream4(pol.op.ys + i) : z;
-            const float4 p = one ? ldg_stream4(pol.op.ps + i) : z, t = (R::kNeedT && one) ? ldg_stream4(pol.op.ts + i) : z;
+            const float4 p = one ? ldg_stream4(pol.op.ps + i) : z, t = one ? ldg_stream4(pol.op.ts + i) : z;
             const float4 x2 = two ? ldg_stream4(pol.op.xs + i2) : z, y2 = two ? ldg_stream4(pol.op.ys + i2) : z;
-            const float4 p2 = two ? ldg_stream4(pol.op.ps + i2) : z, t2 = (R::kNeedT && two) ? ldg_stream4(pol.op.ts + i2) : z;
+            const float4 p2 = two ? ldg_stream4(pol.op.ps + i2) : z, t2 = two ? ldg_stream4(pol.op.ts + i2) : z;
             if (one) {
-                pol.event(bins, role, cur, i + 0, x.x, y.x, t.x, p.x);
-                pol.event(bins, role, cur, i + 1, x.y, y.y, t.y, p.y);
-                pol.event(bins, role, cur, i + 2, x.z, y.z, t.z, p.z);
-                pol.event(bins, role, cur, i + 3, x.w, y.w, t.w, p.w);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i + 0, x.x, y.x, t.x, p.x);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i + 1, x.y, y.y, t.y, p.y);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i + 2, x.z, y.z, t.z, p.z);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i + 3, x.w, y.w, t.w, p.w);
             }
             if (two) {
-                pol.event(bins, role, cur, i2 + 0, x2.x, y2.x, t2.x, p2.x);
-                pol.event(bins, role, cur, i2 + 1, x2.y, y2.y, t2.y, p2.y);
-                pol.event(bins, role, cur, i2 + 2, x2.z, y2.z, t2.z, p2.z);
-                pol.event(bins, role, cur, i2 + 3, x2.w, y2.w, t2.w, p2.w);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i2 + 0, x2.x, y2.x, t2.x, p2.x);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i2 + 1, x2.y, y2.y, t2.y, p2.y);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i2 + 2, x2.z, y2.z, t2.z, p2.z);
+                pol.template event<ROLE, TN>(bins, cur, fcur, fb, i2 + 3, x2.w, y2.w, t2.w, p2.w);
             }
         } else {
-            if (u < u_hi) pol.event(bins, role, cur, u, pol.op.xs[u], pol.op.ys[u], R::kNeedT ? pol.op.ts[u] : 0.f, pol.op.ps[u]);
-            if (u2 < u_hi) pol.event(bins, role, cur, u2, pol.op.xs[u2], pol.op.ys[u2], R::kNeedT ? pol.op.ts[u2] : 0.f, pol.op.ps[u2]);
+            if (u < u_hi) pol.template event<ROLE, TN>(bins, cur, fcur, fb, u, pol.op.xs[u], pol.op.ys[u], pol.op.ts[u], pol.op.ps[u]);
+            if (u2 < u_hi) pol.template event<ROLE, TN>(bins, cur, fcur, fb, u2, pol.op.xs[u2], pol.op.ys[u2], pol.op.ts[u2], pol.op.ps[u2]);
         }
     }
     if (vec_ok && grp == G - 1) {                    // the last n % 4 events
         const long i = (n & ~3L) + tid;
         if (i < n) {
-            const int slot = pol.slot_of(i);
             // (they may belong to another slot than the plane holds: event() then takes the global path in role 0)
-            pol.event(bins, role, slot == cur ? cur : -3, i, pol.op.xs[i], pol.op.ys[i], R::kNeedT ? pol.op.ts[i] : 0.f, pol.op.ps[i]);
+            const bool same = pol.slot_of(i) == cur;
+            pol.template event<ROLE, TN>(bins, cur, same ? fcur : __int_as_float(0x7fc00000), fb, i, pol.op.xs[i], pol.op.ys[i], pol.op.ts[i], pol.op.ps[i]);
         }
     }
     __syncthreads();
-    if (cur >= 0) pol.flush(bins, role, cur);
+    if (cur >= 0) pol.flush(bins, ROLE, cur);
+}
+
+template <class R>
+__global__ void __launch_bounds__(kRoleThreads, 1) role_kernel(R pol, long n, int roles, int vec_ok) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned* bins = reinterpret_cast<unsigned*>(smem_raw);
+    const int role = blockIdx.x % roles, grp = blockIdx.x / roles, G = gridDim.x / roles;
+    for (int k = threadIdx.x; k < pol.words(); k += kRoleThreads) bins[k] = 0u;
+    pol.op.prepare(n);
+    __syncthreads();
+    const bool tn = pol.op.flags & BMC_ENC_TNORM;
+    if (role == 0) { if (tn) role_body<R, 0, true>(pol, bins, n, grp, G, vec_ok); else role_body<R, 0, false>(pol, bins, n, grp, G, vec_ok); }
+    else { if (tn) role_body<R, 1, true>(pol, bins, n, grp, G, vec_ok); else role_body<R, 1, false>(pol, bins, n, grp, G, vec_ok); }
 }
 
 // deferred in-place zeroing of out-of-range events (encodings.py:252-254) after role_kernel
