@@ -708,6 +708,59 @@ struct VoxelRole {
     }
 };
 
+// events_to_channels on grids up to 360x640: role 0 counts the positive events, role 1 the negative ones, each in a plane
+// of 8-bit counters (230,400 B).  A field is advanced by a compare-and-swap: the transition 0xFF -> 0x00 is taken
+// explicitly and credits 256 to the global grid, so the count is exact for any input (a native add would carry into the
+// neighbouring pixel's field, and a threshold scheme has no head-room in 8 bits).  Half of a warp's lanes take the
+// counting path in each role -- against a quarter with four spatial roles, which was measured slower than the L2 path.
+struct CountsRole {
+    static constexpr bool kNeedT = false;
+    ChannelsOp op;                                // flags WITHOUT BMC_ENC_MUTATE
+    int* g_cnt; float* g_ext;
+    OorList oor;
+    int mutate;
+    __device__ __forceinline__ int words() const { return (op.H * op.W + 3) >> 2; }
+    __device__ __forceinline__ int slot_from(float) const { return 0; }
+    __device__ __forceinline__ int slot_of(long) const { return 0; }
+    template <int ROLE, bool TN>
+    __device__ __forceinline__ void event(unsigned* bins, int, float, float, long i, float x, float y, float t, float p) const {
+        const bool in = (x < (float)op.W) & (x >= 0.f) & (y < (float)op.H) & (y >= 0.f);
+        if (in & (p * p == 1.f)) {
+            if ((p < 0.f) != (ROLE == 1)) return;
+            const int pix = (op.H - 1 - (int)y) * op.W + (int)x, sh = (pix & 3) * 8;
+            const uint32_t wa = smem_u32(bins) + (uint32_t)(pix >> 2) * 4u;
+            unsigned old, assumed;
+            asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(old) : "r"(wa) : "memory");
+            bool wrap;
+            do {
+                assumed = old;
+                wrap = ((assumed >> sh) & 0xFFu) == 0xFFu;
+                const unsigned nw = wrap ? assumed & ~(0xFFu << sh) : assumed + (1u << sh);
+                asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(wa), "r"(assumed), "r"(nw) : "memory");
+            } while (old != assumed);
+            if (wrap) atomicAdd(&g_cnt[(ROLE ? op.H * op.W : 0) + pix], 256);
+            return;
+        }
+        if (ROLE != 0) return;                       // out-of-range events (F9 leak, deferred zeroing) and non-unit weights: once
+        if (!in && mutate) oor.add(i);
+        Hist<kGlobal, false> h;
+        h.g_cnt = g_cnt; h.g_ext = g_ext;
+        op.run(h, i, x, y, t, p);
+    }
+    __device__ __forceinline__ void flush(unsigned* bins, int role, int) const {
+        const int plane = op.H * op.W;
+        int* g = g_cnt + (role ? plane : 0);
+        for (int k = threadIdx.x; k < words(); k += kRoleThreads) {
+            const unsigned v = bins[k];
+            if (!v) continue;
+            bins[k] = 0u;
+#pragma unroll
+            for (int f = 0; f < 4; ++f)
+                if (((v >> (8 * f)) & 0xFFu) && 4 * k + f < plane) atomicAdd(&g[4 * k + f], (int)((v >> (8 * f)) & 0xFFu));
+        }
+    }
+};
+
 template <class R, int ROLE, bool TN>
 __device__ __forceinline__ void role_body(R& pol, unsigned* bins, long n, int grp, int G, int vec_ok) {
     const int tid = threadIdx.x;
@@ -721,11 +774,11 @@ __device__ __forceinline__ void role_body(R& pol, unsigned* bins, long n, int gr
     const int w = vec_ok ? 4 : 1;
     // Two units per thread and iteration, all loads issued before the first atomic; the time stamp that decides the NEXT
     // iteration's slot is requested now and looked at after this iteration's events (no dependent load on the path).
-    float t_first = u_lo < u_hi ? pol.op.ts[u_lo * w] : 0.f;
+    float t_first = (R::kNeedT && u_lo < u_hi) ? pol.op.ts[u_lo * w] : 0.f;
     for (long base = u_lo; base < u_hi; base += 2 * kRoleThreads) {
         const int slot = pol.slot_from(t_first);     // uniform: the iteration's first event
         const long nb = base + 2 * kRoleThreads;
-        if (nb < u_hi) t_first = ldg_stream1(pol.op.ts + nb * w);
+        if (R::kNeedT && nb < u_hi) t_first = ldg_stream1(pol.op.ts + nb * w);
         if (slot != cur) {
             __syncthreads();
             if (cur >= 0) pol.flush(bins, ROLE, cur);
@@ -738,9 +791,9 @@ __device__ __forceinline__ void role_body(R& pol, unsigned* bins, long n, int gr
             const bool one = u < u_hi, two = u2 < u_hi;
             const long i = u << 2, i2 = u2 << 2;
             const float4 x = one ? ldg_stream4(pol.op.xs + i) : z, y = one ? ldg_stream4(pol.op.ys + i) : z;
-            const float4 p = one ? ldg_stream4(pol.op.ps + i) : z, t = one ? ldg_stream4(pol.op.ts + i) : z;
+            const float4 p = one ? ldg_stream4(pol.op.ps + i) : z, t = (R::kNeedT && one) ? ldg_stream4(pol.op.ts + i) : z;
             const float4 x2 = two ? ldg_stream4(pol.op.xs + i2) : z, y2 = two ? ldg_stream4(pol.op.ys + i2) : z;
-            const float4 p2 = two ? ldg_stream4(pol.op.ps + i2) : z, t2 = two ? ldg_stream4(pol.op.ts + i2) : z;
+            const float4 p2 = two ? ldg_stream4(pol.op.ps + i2) : z, t2 = (R::kNeedT && two) ? ldg_stream4(pol.op.ts + i2) : z;
             if (one) {
                 pol.template event<ROLE, TN>(bins, cur, fcur, fb, i + 0, x.x, y.x, t.x, p.x);
                 pol.template event<ROLE, TN>(bins, cur, fcur, fb, i + 1, x.y, y.y, t.y, p.y);
@@ -754,8 +807,8 @@ __device__ __forceinline__ void role_body(R& pol, unsigned* bins, long n, int gr
                 pol.template event<ROLE, TN>(bins, cur, fcur, fb, i2 + 3, x2.w, y2.w, t2.w, p2.w);
             }
         } else {
-            if (u < u_hi) pol.template event<ROLE, TN>(bins, cur, fcur, fb, u, pol.op.xs[u], pol.op.ys[u], pol.op.ts[u], pol.op.ps[u]);
-            if (u2 < u_hi) pol.template event<ROLE, TN>(bins, cur, fcur, fb, u2, pol.op.xs[u2], pol.op.ys[u2], pol.op.ts[u2], pol.op.ps[u2]);
+            if (u < u_hi) pol.template event<ROLE, TN>(bins, cur, fcur, fb, u, pol.op.xs[u], pol.op.ys[u], R::kNeedT ? pol.op.ts[u] : 0.f, pol.op.ps[u]);
+            if (u2 < u_hi) pol.template event<ROLE, TN>(bins, cur, fcur, fb, u2, pol.op.xs[u2], pol.op.ys[u2], R::kNeedT ? pol.op.ts[u2] : 0.f, pol.op.ps[u2]);
         }
     }
     if (vec_ok && grp == G - 1) {                    // the last n % 4 events
@@ -763,7 +816,7 @@ __device__ __forceinline__ void role_body(R& pol, unsigned* bins, long n, int gr
         if (i < n) {
             // (they may belong to another slot than the plane holds: event() then takes the global path in role 0)
             const bool same = pol.slot_of(i) == cur;
-            pol.template event<ROLE, TN>(bins, cur, same ? fcur : __int_as_float(0x7fc00000), fb, i, pol.op.xs[i], pol.op.ys[i], pol.op.ts[i], pol.op.ps[i]);
+            pol.template event<ROLE, TN>(bins, cur, same ? fcur : __int_as_float(0x7fc00000), fb, i, pol.op.xs[i], pol.op.ys[i], R::kNeedT ? pol.op.ts[i] : 0.f, pol.op.ps[i]);
         }
     }
     __syncthreads();
@@ -1148,6 +1201,22 @@ extern "C" BMC_EXPORT int bmc_encode_channels(float* xs, float* ys, const float*
     ChannelsOp op;
     op.xs = xs; op.ys = ys; op.ts = nullptr; op.ps = const_cast<float*>(ps);
     op.H = H; op.W = W; op.bins = 1; op.flags = flags | BMC_ENC_FLIP_Y;
+    if (2L * H * W > kMaxBinsSmem16 && (H * W + 3) / 4 <= kRoleWords && (n >= kRoleMinEvents || (flags & BMC_ENC_SPLIT_BINS)) && n > 0 &&
+        roles_enabled()) {
+        CountsRole pol;                     // up to 360x640: one CTA per polarity over the same events, 8-bit counter planes
+        pol.op = op; pol.op.flags &= ~BMC_ENC_MUTATE; pol.mutate = (flags & BMC_ENC_MUTATE) ? 1 : 0;
+        Ws w;
+        cudaStream_t st = as_stream(stream);
+        const long elems = 2L * H * W;
+        rc = carve(workspace, workspace_bytes, elems, w);
+        if (rc) return rc;
+        pol.g_cnt = w.cnt; pol.g_ext = w.ext;
+        rc = run_roles(pol, n, 2, elems, workspace, workspace_bytes, w, st);
+        if (rc) return rc;
+        finalize_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(w.cnt, w.ext, out, elems);
+        BMC_CUDA(cudaGetLastError());
+        return BMC_OK;
+    }
     return run_scatter(op, n, 2L * H * W, out, workspace, workspace_bytes, as_stream(stream));
 }
 
