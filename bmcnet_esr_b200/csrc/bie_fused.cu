@@ -41,7 +41,18 @@
 namespace bmc {
 namespace {
 
-constexpr int kFrontThreads = 384;
+// Epilogue width: 8 warps (two per TMEM lane quarter, 64 accumulator columns per thread) or 16 (four per quarter, 32
+// columns per thread, 640 threads at <= 102 registers).  The LN / C / U passes sit on the tile's dependency chain, so 16
+// warps were tried to shorten every pass: measured 2.7 % SLOWER per plain step (3.84 vs 3.74 ms over 50 steps; BMCNet 12.13 vs
+// 11.96 ms) -- the passes are bound by the TMEM reads and the swizzled shared-memory stores, not by issue slots, and the
+// extra warps compete with the two MMA-issuing threads.  Both widths compile from this source; 8 is the product.
+constexpr int kEpiWarps = 8;
+constexpr int kEpiGroups = kEpiWarps / 4;            // column groups
+constexpr int kEpiCols = 128 / kEpiGroups;           // accumulator columns (channels) per epilogue thread
+constexpr int kEpiNB = kEpiCols / 32;                // 32-column blocks per thread
+constexpr int kEpi0 = kEpiWarps == 8 ? 3 : 4;        // first epilogue warp (a warp reads TMEM lanes 32 (warp % 4) ..)
+constexpr int kMmaWarpB = kEpiWarps == 8 ? 11 : 3;   // second MMA issuer (the first is warp 2)
+constexpr int kFrontThreads = 32 * (kEpi0 + kEpiWarps) + (kEpiWarps == 8 ? 32 : 0);
 constexpr int kTile = 128;
 constexpr int kHalfBytes = kTile * kChunkK * 2;      // one [128 x 64] fp16 box: 16 KB
 constexpr int kTensBytes = 2 * kHalfBytes;           // a 128-channel tile: 32 KB
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     __shared__ uint64_t ln_done[2], c_done[2], a_free, u_done;     // epilogue -> MMA, once per tile each (see the issuers)
     __shared__ uint32_t tmem_base_s;
     __shared__ __align__(16) float bias_f[128], bias_c[128], bias_u[128];
-    __shared__ float ln_sum[2][2][128], ln_var[2][2][128];     // [pass A / B][column half][row]
+    __shared__ float ln_sum[2][kEpiGroups][128], ln_var[2][kEpiGroups][128];     // [pass A / B][column group][row]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tpi = p.tiles_per_img;
@@ -107,8 +118,8 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
     if (threadIdx.x == 0) {
         mbar_init(&in_full, 1); mbar_init(&in_empty, 2);
         for (int s = 0; s < kFrontWStages; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
-        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&ln_done[s], 8); mbar_init(&c_done[s], 8); }
-        mbar_init(&acc_full[2], 2); mbar_init(&a_free, 8); mbar_init(&u_done, 8);
+        for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&ln_done[s], kEpiWarps); mbar_init(&c_done[s], kEpiWarps); }
+        mbar_init(&acc_full[2], 2); mbar_init(&a_free, kEpiWarps); mbar_init(&u_done, kEpiWarps);
         mbar_fence_init();
         tma_prefetch_desc(&p.map_act);
         tma_prefetch_desc(&p.map_w);
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 }
             }
         }
-    } else if (warp == 2 || warp == 11) {
+    } else if (warp == 2 || warp == kMmaWarpB) {
         // ------------------------------------------------------------ MMA issuers
         // Two issuing threads (a lone one cannot keep the tensor pipe busy, see gemm_slab.cu): role 0 owns
         // accumulator A (Y1, C1, att1, U), role 1 owns B (Y2, C2, att2, s).  Shared resources (weight
@@ -311,12 +322,12 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
         }
     } else {
         // ------------------------------------------------------------ epilogue (warps 3..10)
-        const int e = warp - 3;
-        const int ch = e >> 2;                     // column half: channels [64 ch, 64 ch + 64)
+        const int e = warp - kEpi0;
+        const int ch = e >> 2;                     // column group: channels [kEpiCols ch, kEpiCols ch + kEpiCols)
         const int q = warp & 3;                    // TMEM lane quarter this warp may read
         const int r = q * 32 + lane;               // row of the tile
         const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-        const int tt = threadIdx.x - 96;           // 0..255
+        const int tt = threadIdx.x - 32 * kEpi0;   // 0 .. 32 kEpiWarps - 1
         uint32_t acc_uses[3] = {0, 0, 0};
         float s_run = 0.f;                         // running sum_px c_k[px, c] for k = ch, c = r
         bool store_pending = false;                // this thread has an x_s' bulk store whose smem reads may be in flight
@@ -345,45 +356,48 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             for (int a = 0; a < 2; ++a) {
                 wait_acc(a);
                 const long long _tp = prof_on ? clock64() : 0;
-                const uint32_t trow = tmem_base + a * 128 + lane_off + ch * 64;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(trow, v0);
-                tmem_ld_32x32(trow + 32, v1);
+                const uint32_t trow = tmem_base + a * 128 + lane_off + ch * kEpiCols;
+                uint32_t v[kEpiNB][32];
+#pragma unroll
+                for (int h = 0; h < kEpiNB; ++h) tmem_ld_32x32(trow + 32 * h, v[h]);
                 tmem_ld_wait();
-                // One pass over the 64 values of this thread: x = acc + bias, sum and sum of squares.  The two threads
-                // of a row (column halves, warps q and q + 4) exchange their partial moments once (a 64-thread named
-                // barrier per lane quarter).  var = E[x^2] - mu^2 in fp32 over 128 channels: the cancellation costs
-                // ~2^-24 * mu^2 / var relative, negligible against the fp16 rounding of the output.
+                // One pass over the values of this thread: x = acc + bias, sum and sum of squares.  The threads of a row
+                // (one per column group, warps q, q + 4, ...) exchange their partial moments once (a named barrier per
+                // lane quarter) and add them in a fixed order.  var = E[x^2] - mu^2 in fp32 over 128 channels: the
+                // cancellation costs ~2^-24 * mu^2 / var relative, negligible against the fp16 rounding of the output.
                 // gamma and beta are NOT applied here: they are folded into the clustering weights / bias
                 // (model.cu, `clustering_ln`), so the normalisation is one FMA per element.
                 float sum = 0.f, sq = 0.f;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float x0 = __uint_as_float(v0[j]) + bias_f[ch * 64 + j];
-                    const float x1 = __uint_as_float(v1[j]) + bias_f[ch * 64 + 32 + j];
-                    v0[j] = __float_as_uint(x0); v1[j] = __float_as_uint(x1);
-                    sum += x0 + x1;
-                    sq = fmaf(x0, x0, sq);
-                    sq = fmaf(x1, x1, sq);
-                }
+                for (int h = 0; h < kEpiNB; ++h)
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float x0 = __uint_as_float(v[h][j]) + bias_f[ch * kEpiCols + 32 * h + j];
+                        v[h][j] = __float_as_uint(x0);
+                        sum += x0;
+                        sq = fmaf(x0, x0, sq);
+                    }
                 ln_sum[a][ch][r] = sum;
                 ln_var[a][ch][r] = sq;
                 // (the quarter's store thread first makes sure the previous tile's bulk store has read its s_y rows)
                 if (a == 0 && store_pending) { tma_store_wait_read<0>(); store_pending = false; }
-                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-                const float mu = (sum + ln_sum[a][ch ^ 1][r]) * (1.f / 128.f);
-                const float var = fmaxf((sq + ln_var[a][ch ^ 1][r]) * (1.f / 128.f) - mu * mu, 0.f);
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kEpiGroups) : "memory");
+                float tsum = 0.f, tsq = 0.f;
+#pragma unroll
+                for (int g2 = 0; g2 < kEpiGroups; ++g2) { tsum += ln_sum[a][g2][r]; tsq += ln_var[a][g2][r]; }
+                const float mu = tsum * (1.f / 128.f);
+                const float var = fmaxf(tsq * (1.f / 128.f) - mu * mu, 0.f);
                 const float rstd = rsqrtf(var + p.ln_eps);
                 const float nb = -mu * rstd;
                 // (buffers alternate between the A and the B pass: the barrier of the next pass orders the reuse)
                 uint8_t* dst = a == 0 ? s_y : s_xs;
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v0[j]), rstd, nb);
-                store_tile_row32(dst, r, ch * 2, f);
+                for (int h = 0; h < kEpiNB; ++h) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v1[j]), rstd, nb);
-                store_tile_row32(dst, r, ch * 2 + 1, f);
+                    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[h][j]), rstd, nb);
+                    store_tile_row32(dst, r, ch * kEpiNB + h, f);
+                }
                 phase_done(&ln_done[a], true);
                 if (prof_on) pe_ln += clock64() - _tp;
             }
@@ -392,19 +406,19 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
             for (int a = 0; a < 2; ++a) {
                 wait_acc(a);
                 const long long _tp = prof_on ? clock64() : 0;
-                const uint32_t trow = tmem_base + a * 128 + lane_off + ch * 64;
-                uint32_t v0[32], v1[32];
-                tmem_ld_32x32(trow, v0);
-                tmem_ld_32x32(trow + 32, v1);
+                const uint32_t trow = tmem_base + a * 128 + lane_off + ch * kEpiCols;
+                uint32_t v[kEpiNB][32];
+#pragma unroll
+                for (int h = 0; h < kEpiNB; ++h) tmem_ld_32x32(trow + 32 * h, v[h]);
                 tmem_ld_wait();
                 uint8_t* dst = a == 0 ? s_y : s_xs;
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v0[j]) + bias_c[ch * 64 + j] : 0.f;
-                store_tile_row32(dst, r, ch * 2, f);
+                for (int h = 0; h < kEpiNB; ++h) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v1[j]) + bias_c[ch * 64 + 32 + j] : 0.f;
-                store_tile_row32(dst, r, ch * 2 + 1, f);
+                    for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[h][j]) + bias_c[ch * kEpiCols + 32 * h + j] : 0.f;
+                    store_tile_row32(dst, r, ch * kEpiNB + h, f);
+                }
                 phase_done(&c_done[a], true);
                 if (prof_on) pe_c += clock64() - _tp;
             }
@@ -418,24 +432,26 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 const BieInst& in = p.inst[inst];
                 wait_acc(2);
                 const long long _tp = prof_on ? clock64() : 0;
-                uint32_t v0[32], v1[32], sv;
-                tmem_ld_32x32_x1(tmem_base + lane_off + 16 * ch, sv);         // s_k: column 0 of A[16 k .. 16 k + 15]
-                tmem_ld_wait();
+                uint32_t v[kEpiNB][32], sv = 0u;
+                if (ch < 2) {                                                 // s_k: column 0 of A[16 k .. 16 k + 15], k = ch
+                    tmem_ld_32x32_x1(tmem_base + lane_off + 16 * ch, sv);
+                    tmem_ld_wait();
+                }
                 phase_done(&a_free, false);                                   // A may take the next tile's Y1 now
                 s_run += __uint_as_float(sv);
-                const uint32_t trow = tmem_base + 128 + lane_off + ch * 64;   // U lives in B
-                tmem_ld_32x32(trow, v0);
-                tmem_ld_32x32(trow + 32, v1);
+                const uint32_t trow = tmem_base + 128 + lane_off + ch * kEpiCols;   // U lives in B
+#pragma unroll
+                for (int h = 0; h < kEpiNB; ++h) tmem_ld_32x32(trow + 32 * h, v[h]);
                 tmem_ld_wait();
                 float f[32];
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v0[j]) + bias_u[ch * 64 + j] : 0.f;
-                store_tile_row32(s_y, r, ch * 2, f);
+                for (int h = 0; h < kEpiNB; ++h) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v1[j]) + bias_u[ch * 64 + 32 + j] : 0.f;
-                store_tile_row32(s_y, r, ch * 2 + 1, f);
+                    for (int j = 0; j < 32; ++j) f[j] = valid ? __uint_as_float(v[h][j]) + bias_u[ch * kEpiCols + 32 * h + j] : 0.f;
+                    store_tile_row32(s_y, r, ch * kEpiNB + h, f);
+                }
                 fence_proxy_async_smem();
-                asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+                asm volatile("bar.sync %0, %1;" ::"r"(2 + q), "n"(32 * kEpiGroups) : "memory");
                 if (ch == 0 && lane == 0) {
                     const int grow = in.out_row + b * R + t * kTile + q * 32;
                     tma_reduce_add_2d(&p.map_out, s_y + q * 4096, 0, grow);
@@ -451,10 +467,12 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                 // its MMAs) and s_k go to this CTA's next partial slot.  Each warp transposes its
                 // [32 rows x 32 cols] fp32 blocks through a private 4 KB tile so rows leave as full lines.
                 const long long _tp = prof_on ? clock64() : 0;
-                asm volatile("bar.sync 1, 256;" ::: "memory");             // every warp is done with its store staging
-                float* tile = reinterpret_cast<float*>(s_y + e * 4096);
+                asm volatile("bar.sync 1, %0;" ::"n"(32 * kEpiWarps) : "memory");      // every warp is done with its store staging
+                // (eight warps -- the column groups 0 and 1 -- do the flush: s_y holds eight 4 KB transposition tiles, and
+                // the other input tiles may already be receiving the next tile; it runs once per image and CTA)
+                float* tile = reinterpret_cast<float*>(s_y + (e & 7) * 4096);
 #pragma unroll 1
-                for (int kc = 0; kc < 4; ++kc) {
+                for (int kc = 0; kc < (ch < 2 ? 4 : 0); ++kc) {
                     const int k = kc >> 1, c = ch * 2 + (kc & 1);          // att_k, columns [32 c, 32 c + 32)
                     uint32_t v[32];
                     tmem_ld_32x32(tmem_base + 256 + k * 128 + lane_off + c * 32, v);
@@ -473,7 +491,7 @@ __global__ void __launch_bounds__(kFrontThreads, 1) bie_front_tc(const __grid_co
                     }
                     __syncwarp();
                 }
-                p.s_partial[(long)slot * 256 + ch * 128 + r] = s_run;
+                if (ch < 2) p.s_partial[(long)slot * 256 + ch * 128 + r] = s_run;
                 s_run = 0.f;
                 ++slot;
                 if (prof_on) pe_flush += clock64() - _tp;
