@@ -81,6 +81,7 @@ class _Ctx:
         self.ws = None
         self.ln_ws = None
         self.side = None          # GraphedIteration: the stream the weight-gradient kernels are recorded on
+        self.keep = []            # gradient tensors the side stream reads (see _ConvFn.backward)
 
     def workspace(self, dev):
         nbytes = lib().bmc_conv_wgrad_workspace_bytes(WGRAD_SPLITS, 9, 128)
@@ -186,21 +187,29 @@ class _ConvFn(torch.autograd.Function):
         gb = _grad_buf(conv.bias)
         inv = 1.0 / tc.loss_scale
 
-        def wgrads():
+        def wgrads(dy):
             for i, (src, idx) in enumerate(zip(srcs, segs)):
-                K.conv_wgrad(dz, src, taps, b, h, w, tc.cmap(idx, dev), conv.in_channels, conv.out_channels, inv,
+                K.conv_wgrad(dy, src, taps, b, h, w, tc.cmap(idx, dev), conv.in_channels, conv.out_channels, inv,
                              gw, gb if (i == 0 and ctx.use_bias) else None, ws, WGRAD_SPLITS)
 
         if tc.side is None:
-            wgrads()
+            wgrads(dz)
         else:
             # Nothing downstream in the backward pass reads a weight gradient, so inside a captured iteration the wgrad
             # kernels go to ONE side stream (they stay ordered among themselves: shared workspace, aliased gradient
             # buffers) and overlap the dgrad chain, which at training batches fills a fifth of the SMs.
+            # Without a ReLU `dz` IS the incoming gradient tensor (the backward of `x + conv(t)` hands the same tensor to
+            # both addends), and the autograd engine accumulates further gradients into such a buffer IN PLACE on the main
+            # stream once it holds the last reference (input_buffer.cpp: use_count() == 1) -- while the side stream may
+            # still be reading it.  Holding a reference until the iteration's backward is over keeps the engine on the
+            # out-of-place path for this tensor (same number of kernels, no copy).
+            wg_dz = dz
+            if not ctx.relu:
+                tc.keep.append(dz)
             tc.side.wait_stream(torch.cuda.current_stream(dev))
             with torch.cuda.stream(tc.side):
-                wgrads()
-            for t in (dz, *srcs):
+                wgrads(wg_dz)
+            for t in (wg_dz, *srcs):
                 t.record_stream(tc.side)
         grads = []
         for i, src in enumerate(srcs):
@@ -606,6 +615,7 @@ class GraphedIteration:
                 pred = F.interpolate(pred, size=gt.shape[-2:], mode='bicubic', align_corners=False)
             loss = loss + F.mse_loss(pred, gt)
         loss.backward()
+        context(m).keep.clear()
         return loss.detach()
 
     def __call__(self, xs=None, gts=None):

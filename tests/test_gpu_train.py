@@ -260,3 +260,34 @@ def test_graphed_iteration_matches_eager(plain, plain_ckpt):
         assert d.max().item() <= 0.3 * lr and d.mean().item() <= 0.01 * lr, (n, d.max().item(), d.mean().item())
     moved = max((p.detach().cpu() - sd[n]).abs().max().item() for n, p in m_g.named_parameters() if n in sd)
     assert moved >= 2 * lr            # three Adam steps did move the weights
+
+
+def test_graphed_iteration_side_stream_is_exact_and_reproducible(plain_ckpt):
+    """The weight-gradient kernels of a captured iteration run on a side stream.  Gradient tensors they read must not be
+    updated in place by the autograd engine meanwhile (models/_train.py, _ConvFn.backward): with and without the side
+    stream, and from run to run, the flat gradient buffer is bit-identical over three iterations."""
+    from bmcnet_esr_b200.models.BMCNet import BMCNet
+    from bmcnet_esr_b200.models._train import FusedAdamAMSGrad, GraphedIteration
+    b, h, w, steps = 2, 22, 40, 3
+    sd = O.surrogate_state_dict(plain=False, seed=2024, transplant=plain_ckpt)
+    xs = [synth_counts(b, h, w, 900 + s).cuda() for s in range(steps)]
+    g = torch.Generator().manual_seed(3)
+    gts = [torch.poisson(torch.full((b, 2, 4 * h, 4 * w), 0.3), generator=g).cuda() for _ in range(steps)]
+
+    def run(side):
+        m = BMCNet(4, 128, 5)
+        m.load_state_dict({k: v.clone() for k, v in sd.items()}, strict=True)
+        m = m.cuda().train()
+        opt = FusedAdamAMSGrad(m.parameters())
+        it = GraphedIteration(m, opt, xs, gts, wgrad_stream=side)
+        out = []
+        for _ in range(3):
+            loss = it().item()
+            out.append((loss, opt.grad.clone()))
+        return out
+
+    a, a2, c = run(True), run(True), run(False)
+    for (la, ga), (la2, ga2), (lc, gc) in zip(a, a2, c):
+        assert la == la2 == lc
+        assert torch.equal(ga, ga2) and torch.equal(ga, gc)
+    assert a[0][0] != a[1][0]
