@@ -162,3 +162,33 @@ def layernorm_rows_backward(x, dy, gamma, eps, scale, grad_gamma, grad_beta, wor
                                                 grad_gamma.data_ptr(), grad_beta.data_ptr(), workspace.data_ptr(),
                                                 workspace.numel(), stream_ptr()))
     return dx
+
+
+def conv_gemm_stack(srcs, slabs, wstack, biases, n_jobs, b, h, w, taps, relu=False):
+    """J = n_jobs convolutions of one shape in ONE launch (bmc_conv_gemm with n_jobs jobs) on STACKED operands, so that
+    the launch needs three or four tensor maps whatever J is:
+      srcs[s]    packed act16 [n_slabs_s * rows, C_s]: segment s of job j reads slab slabs[s][j] (rows = B * R)
+      wstack     act16 [K/64, J*128, 64]: the J chunk-major weight matrices side by side (job j = rows j*128 .. j*128+127)
+      biases     list of J fp32 [128] tensors, or None
+    Returns act16 [J * rows, 128], job j in slab j."""
+    rows = b * rows_per_image(h, w)
+    dev = srcs[0].device
+    out = torch.empty(n_jobs * rows, 128, dtype=_lib.act_dtype(), device=dev)
+    jobs = (GemmJob * n_jobs)()
+    keep = []
+    for jn in range(n_jobs):
+        j = jobs[jn]
+        j.n_seg = len(srcs)
+        for i, s in enumerate(srcs):
+            j.a[i] = s.data_ptr(); j.a_rows[i] = s.shape[0]; j.a_ch[i] = s.shape[1]; j.a_row_base[i] = slabs[i][jn] * rows
+        j.w = wstack.data_ptr(); j.w_rows = wstack.shape[1]; j.w_k = wstack.shape[0] * 64
+        j.w_row_base = jn * 128; j.w_img_stride = 0
+        if biases is not None:
+            bt = biases[jn].contiguous().float()
+            keep.append(bt)
+            j.bias = bt.data_ptr()
+        j.out_act16 = out.data_ptr(); j.out_row_base = jn * rows
+        j.relu = int(relu)
+    with _need_cuda(*srcs, wstack, *keep):
+        check(lib().bmc_conv_gemm(jobs, n_jobs, 128, taps, b, h, w, 0, stream_ptr()))
+    return out

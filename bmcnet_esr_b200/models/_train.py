@@ -35,6 +35,12 @@ from .. import _lib, kernels as K
 from .._lib import check, lib, stream_ptr
 
 WGRAD_SPLITS = 16
+STACKED = True       # independent convolutions of one shape as multi-job launches on stacked tensors (conv_stack) while one
+                     # job fills at most half a wave of SMs (else one launch each: the gather copies cost more than they save)
+
+
+def _use_stack(b, h, w):
+    return STACKED and 2 * b * K.rows_per_image(h, w) <= 256 * 148
 DEFAULT_LOSS_SCALE = 2.0 ** 14
 
 
@@ -100,6 +106,12 @@ class _Ctx:
             self.cmaps[key] = torch.tensor(idx, dtype=torch.int32, device=dev)
         return self.cmaps[key]
 
+    def lidx(self, idx, dev):
+        key = ('l', tuple(idx), str(dev))
+        if key not in self.cmaps:
+            self.cmaps[key] = torch.tensor(idx, dtype=torch.int64, device=dev)
+        return self.cmaps[key]
+
     def gather_index(self, idx, dev):
         """(clamped int64 index, fp32 0/1 mask [1,c,1,1]) of a channel list; cached, so that packing weights issues no
         host-to-device copy (a CUDA-graph capture of the iteration, GraphedIteration, must not contain one)."""
@@ -143,6 +155,16 @@ class _Ctx:
         out = wk.reshape(128, k // 64, 64).permute(1, 0, 2).contiguous().to(_lib.act_dtype())
         self.wcache[key] = out
         return out
+
+
+def _packed_stack(tc, convs, segs, mode, seg=None):
+    """The packs of J convolutions of one shape side by side: act16 [K/64, J*128, 64] (K.conv_gemm_stack)."""
+    key = ('stack', tuple((id(c.weight), c.weight._version) for c in convs), tuple(map(tuple, segs)), mode, seg)
+    hit = tc.wcache.get(key)
+    if hit is None:
+        hit = torch.cat([tc.packed_weight(c.weight, segs, mode, seg) for c in convs], 1).contiguous()
+        tc.wcache[key] = hit
+    return hit
 
 
 def _grad_buf(p):
@@ -232,6 +254,120 @@ def conv(tc, module, srcs, segs, geom, relu=False):
     c = _ConvFn.apply(module.weight, tc, module, segs[3:], False, False, geom, *srcs[3:])
     out = a + c
     return F.relu(out) if relu else out
+
+
+class _ConvStackFn(torch.autograd.Function):
+    """J convolutions of one shape (different weights, or one weight applied to J inputs) as ONE multi-job launch, forward
+    and data-gradient alike, on stacked operands: source tensor s is [n_slabs_s * rows, C_s] and segment s of job j reads
+    slab `slabs[s][j]`; the result is [J * rows, 128].  At training batches one job fills a fifth of the SMs and its
+    launch costs the one-wave floor (14 us): four jobs per launch cost the same.  Weight gradients: per job, as _ConvFn."""
+
+    @staticmethod
+    def forward(ctx, tc, convs, segs, slabs, relu, geom, n_w, *tensors):
+        b, h, w = geom
+        srcs = [t.contiguous() for t in tensors[n_w:]]
+        taps = convs[0].kernel_size[0] * convs[0].kernel_size[1]
+        wst = _packed_stack(tc, convs, segs, 'fwd')
+        biases = []
+        for c in convs:
+            bias = c.bias.detach().float()
+            biases.append(F.pad(bias, (0, 128 - c.out_channels)) if c.out_channels < 128 else bias)
+        out = K.conv_gemm_stack(srcs, slabs, wst, biases, len(convs), b, h, w, taps, relu=relu)
+        ctx.tc, ctx.convs, ctx.segs, ctx.slabs, ctx.relu, ctx.geom, ctx.taps, ctx.n_w = tc, convs, segs, slabs, relu, geom, taps, n_w
+        ctx.save_for_backward(out if relu else None, *srcs)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        tc, convs, segs, slabs, geom, taps = ctx.tc, ctx.convs, ctx.segs, ctx.slabs, ctx.geom, ctx.taps
+        b, h, w = geom
+        out, *srcs = ctx.saved_tensors
+        J = len(convs)
+        rows = b * K.rows_per_image(h, w)
+        dz = dout.contiguous()
+        dev = dz.device
+        if ctx.relu:
+            dz = K.relu_backward(dz, out)
+        ws = tc.workspace(dev)
+        inv = 1.0 / tc.loss_scale
+
+        def wgrads(dy):
+            for j, c in enumerate(convs):
+                gw, gb = _grad_buf(c.weight), _grad_buf(c.bias)
+                dyj = dy[j * rows:(j + 1) * rows]
+                for i, (src, idx) in enumerate(zip(srcs, segs)):
+                    sl = slabs[i][j]
+                    K.conv_wgrad(dyj, src[sl * rows:(sl + 1) * rows], taps, b, h, w, tc.cmap(idx, dev), c.in_channels,
+                                 c.out_channels, inv, gw, gb if i == 0 else None, ws, WGRAD_SPLITS)
+
+        if tc.side is None:
+            wgrads(dz)
+        else:                                   # see _ConvFn.backward
+            if not ctx.relu:
+                tc.keep.append(dz)
+            tc.side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(tc.side):
+                wgrads(dz)
+            for t in (dz, *srcs):
+                t.record_stream(tc.side)
+        grads = []
+        ident = list(range(J))
+        for i, src in enumerate(srcs):
+            if not ctx.needs_input_grad[7 + ctx.n_w + i]:
+                grads.append(None)
+                continue
+            wt = _packed_stack(tc, convs, segs, 'bwd', i)
+            g = K.conv_gemm_stack([dz], [ident], wt, None, J, b, h, w, taps)             # [J * rows, 128]
+            c = src.shape[1]
+            if c != 128:
+                g = g[:, :c]
+            n_slabs = src.shape[0] // rows
+            if slabs[i] == list(range(n_slabs)):
+                grads.append(g.contiguous())
+            else:                                                                          # slabs read by several jobs add up
+                gs = torch.zeros(n_slabs, rows, c, dtype=g.dtype, device=dev)
+                gs.index_add_(0, tc.cmap(slabs[i], dev), g.reshape(J, rows, c))
+                grads.append(gs.view(n_slabs * rows, c))
+        return (None, None, None, None, None, None, None) + (None,) * ctx.n_w + tuple(grads)
+
+
+def conv_stack(tc, convs, srcs, segs, slabs, geom, relu=False):
+    """convs[j](cat of the slabs slabs[s][j] of srcs[s]) for all j in one launch -> [J * rows, 128]."""
+    ws = [c.weight for c in convs]
+    return _ConvStackFn.apply(tc, convs, segs, slabs, relu, geom, len(ws), *ws, *srcs)
+
+
+def resblock_stack(tc, mods, x, geom):
+    """ResidualBlock_noBN mods[j] on slab j of x."""
+    ident = [list(range(len(mods)))]
+    t = conv_stack(tc, [m.conv1 for m in mods], [x], [_R128], ident, geom, relu=True)
+    return x + conv_stack(tc, [m.conv2 for m in mods], [t], [_R128], ident, geom)
+
+
+def _take(tc, x, idx, rows):
+    """slabs `idx` (a list) of a stacked tensor (differentiable gather copy)."""
+    return x.view(-1, rows, x.shape[1]).index_select(0, tc.lidx(idx, x.device)).reshape(len(idx) * rows, x.shape[1])
+
+
+def bie_stack(tc, m, x, xs, n_inst, geom):
+    """BIE.forward (submodules.py:58-77) for n_inst independent instances sharing the module's weights.
+    x: [2 n_inst * rows, 128] = (x1, x2) per instance; xs: [n_inst * rows, 128].  Returns (x1', x2') stacked like x, and xs'."""
+    b, h, w = geom
+    r = K.rows_per_image(h, w)
+    rows = b * r
+    J = 2 * n_inst
+    two = [_R128, _seg(128)]
+    ident = list(range(J))
+    res = resblock_stack(tc, [m.conv1, m.conv2] * n_inst, x, geom)                       # (Res(x1), Res(x2)) per instance
+    # centres_k = clustering(LN(convf_k([x_s, x_other])))
+    u = conv_stack(tc, [m.convf1, m.convf2] * n_inst, [xs, x], two,
+                   [[i // 2 for i in ident], [i ^ 1 for i in ident]], geom)
+    c = conv_stack(tc, [m.clustering] * J, [layernorm_rows(tc, m.norm_s, u)], [_R128], [ident], geom)
+    v = conv_stack(tc, [m.v1, m.v2] * n_inst, [x], [_R128], [ident], geom)
+    o = _AttendFn.apply(c, v, J * b, r, float(m.scale))                                    # every (instance, k, image) on its own
+    ns = conv_stack(tc, [m.unclustering] * n_inst, [c, c], two,
+                    [[2 * i for i in range(n_inst)], [2 * i + 1 for i in range(n_inst)]], geom) + xs
+    return o + _take(tc, res, [i ^ 1 for i in ident], rows), ns                                                   # (out_1 + Res(x_2), out_2 + Res(x_1))
 
 
 _R128 = list(range(128))
@@ -386,8 +522,15 @@ def forward_plain(model, tc, x, x_h, x_o, init):
     seg_s = list(range(2 * n6)) + list(range(2 * n6 + 128, 2 * n6 + 128 + 2 * k))
     seg_s += [-1] * (64 - len(seg_s))
     xs = conv(tc, nb.conv_fs, [hs, ms], [_seg(2 * n6), seg_s], geom, relu=True)
-    for blk in nb.para_reschunk:
-        x1, x2, xs = bie(tc, blk, x1, x2, xs, geom)
+    if _use_stack(b, h, w):
+        rows = b * K.rows_per_image(h, w)
+        x12 = torch.cat([x1, x2], 0)
+        for blk in nb.para_reschunk:
+            x12, xs = bie_stack(tc, blk, x12, xs, 1, geom)
+        x1, x2 = x12[:rows], x12[rows:]
+    else:
+        for blk in nb.para_reschunk:
+            x1, x2, xs = bie(tc, blk, x1, x2, xs, geom)
     n_h = conv(tc, nb.conv_h, [xs], [_R128], geom, relu=True)
     a_o = conv(tc, nb.conv_o, [x1, x2], [_R128, _seg(128)], geom)
     pred = _reconstruct(_ScaleGrad.apply(a_o, tc.loss_scale), f2, geom, sc)
@@ -422,6 +565,23 @@ def forward_full(model, tc, x, x_h, x_h_p, x_h_n, x_o, init):
     seg_o = _seg(384, 2 * k, 64)
     fs = lambda hx: conv(tc, nb.conv_fs, [xp_st, xn_st, hx, mo], [_R128, _seg(128), _seg(256), seg_o], geom, relu=True)
     xs, xs_p, xs_n = fs(hs), fs(hp), fs(hn)
+    if _use_stack(b, h, w):
+        # ParallelBlk (BMCNet.py:19-32) on stacked operands: S = (xp_s, xn_s, xp_st, xn_st), PN = (xs_p, xs_n).  The four
+        # ResidualBlocks are one 4-job launch per convolution, lBIE on the positive and the negative triple shares every
+        # launch (same weights, two instances), gBIE is one instance.
+        rows = b * K.rows_per_image(h, w)
+        S = torch.cat([xp_s, xn_s, xp_st, xn_st], 0)
+        PN = torch.cat([xs_p, xs_n], 0)
+        for blk in nb.para_reschunk:
+            S = resblock_stack(tc, [blk.conv1, blk.conv2, blk.conv1_st, blk.conv2_st], S, geom)
+            X, PN = bie_stack(tc, blk.lBIE, _take(tc, S, [0, 2, 1, 3], rows), PN, 2, geom)     # (xp_s, xp_st, xn_s, xn_st)'
+            G, xs = bie_stack(tc, blk.gBIE, _take(tc, X, [0, 2], rows), xs, 1, geom)           # (xp_s, xn_s)''
+            S = torch.cat([G, _take(tc, X, [1, 3], rows)], 0)
+        hsn = conv_stack(tc, [nb.conv_hs, nb.conv_hp, nb.conv_hn], [torch.cat([xs, PN], 0)], [_R128], [[0, 1, 2]], geom, relu=True)
+        n_h, n_hp, n_hn = hsn[:rows], hsn[rows:2 * rows], hsn[2 * rows:]
+        a_o = conv(tc, nb.conv_o, [S[:rows], S[rows:2 * rows]], [_R128, _seg(128)], geom)
+        pred = _reconstruct(_ScaleGrad.apply(a_o, tc.loss_scale), f2, geom, sc)
+        return _state_out(n_h, geom, tc), _state_out(n_hp, geom, tc), _state_out(n_hn, geom, tc), pred
     for blk in nb.para_reschunk:
         xp_s = resblock(tc, blk.conv1, xp_s, geom)
         xn_s = resblock(tc, blk.conv2, xn_s, geom)

@@ -60,6 +60,17 @@ def fake_conv_gemm(srcs, wpk, bias, b, h, w, taps, n=128, relu=False, residual=N
     return out.to(srcs[0].dtype)
 
 
+def fake_conv_gemm_stack(srcs, slabs, wstack, biases, n_jobs, b, h, w, taps, relu=False):
+    from bmcnet_esr_b200 import kernels as K
+    rows = b * K.rows_per_image(h, w)
+    outs = []
+    for j in range(n_jobs):
+        wj = wstack[:, j * 128:(j + 1) * 128]
+        sj = [s[slabs[i][j] * rows:(slabs[i][j] + 1) * rows] for i, s in enumerate(srcs)]
+        outs.append(fake_conv_gemm(sj, wj, None if biases is None else biases[j], b, h, w, taps, relu=relu))
+    return torch.cat(outs, 0)
+
+
 def fake_conv_wgrad(dy, x, taps, b, h, w, cmap, cin_total, n_out, scale, grad_w, grad_b, workspace, n_split):
     offs = _tap_offsets(taps, w)
     keep = cmap >= 0
@@ -101,6 +112,7 @@ def fake_kernels(monkeypatch):
     from bmcnet_esr_b200 import _lib, kernels as K
     monkeypatch.setattr(_lib, 'act_dtype', lambda: torch.float32)
     monkeypatch.setattr(K, 'conv_gemm', fake_conv_gemm)
+    monkeypatch.setattr(K, 'conv_gemm_stack', fake_conv_gemm_stack)
     monkeypatch.setattr(K, 'conv_wgrad', fake_conv_wgrad)
     monkeypatch.setattr(K, 'relu_backward', fake_relu_backward)
     monkeypatch.setattr(K, 'layernorm_rows', fake_layernorm_rows)
@@ -114,8 +126,12 @@ def _grads_of(model):
     return names
 
 
+@pytest.mark.parametrize('stacked', [True, False])
 @pytest.mark.parametrize('plain', [True, False])
-def test_training_graph_matches_autograd_oracle(fake_kernels, plain):
+def test_training_graph_matches_autograd_oracle(fake_kernels, plain, stacked, monkeypatch):
+    # both launch structures: independent convolutions stacked into multi-job launches (small batches) / one launch each
+    from bmcnet_esr_b200.models import _train as TR
+    monkeypatch.setattr(TR, 'STACKED', stacked)
     from bmcnet_esr_b200.models.BMCNet import BMCNet
     from bmcnet_esr_b200.models.BMCNet_plain import BMCNet_plain
     b, h, w, steps = 2, 6, 9, 2
