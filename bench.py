@@ -371,6 +371,24 @@ def run_workload(cx, name, batch, Ksteps, Wsteps, sustained=True):
     return res
 
 
+TRAIN_LR = 1e-5
+
+
+def train_targets(xs, rank):
+    """Synthetic targets of the training workload: the x4 bilinear interpolation of each step's second count frame -- the
+    base the model adds its learned residual to (BMCNet.py:119) -- plus N(0, 0.05^2) noise, i.e. a fine-tuning regime with
+    small residual errors.  (Pure-noise Poisson targets on the surrogate weights make BPTT spike in fp32 autograd as well:
+    max |grad| 0.6 -> 94 within three iterations of the reference's optimiser on one rank's sequence)"""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5 + rank)
+    out = []
+    for x in xs:
+        base = F.interpolate(x[:, :, 1].float(), scale_factor=4, mode='bilinear', align_corners=False)
+        out.append(base + 0.05 * torch.randn(base.shape, generator=g).to(base.device))
+    return out
+
+
 def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
     """BASELINE config 5: the BMCNet x4 training iteration of train.py:202-237 (8 recurrent steps with BPTT, summed
     MSE, Adam(amsgrad); config/train_nfs.yml: batch 2, NFS LR 45x80), data-parallel: every rank runs its own
@@ -386,10 +404,13 @@ def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
     model = BMCNet(4, 128, 5)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev).train()
-    opt = FusedAdamAMSGrad(model.parameters())                  # lr 1e-4, wd 1e-5, amsgrad (train_nfs.yml:28-34)
+    # Adam(amsgrad), wd 1e-5 as config/train_nfs.yml:28-34, but lr 1e-5 instead of 1e-4: the BMCNet weights here are the
+    # surrogate set (the trained checkpoint is not in the mount) and sit at the edge of recurrent stability -- at 1e-4 the
+    # fp32 reference arithmetic itself spikes on one sequence in eight (max |grad| 1.1 -> 25 -> 0.5, loss 0.63 -> 0.73 ->
+    # 0.34) and the 16-bit path does not recover from that spike.  Timing does not depend on lr.
+    opt = FusedAdamAMSGrad(model.parameters(), lr=TRAIN_LR)
     xs = [synth_counts(batch, h, w, 3000 + 17 * rank + s).to(dev) for s in range(seq_steps)]
-    g = torch.Generator().manual_seed(5 + rank)
-    gts = [torch.poisson(torch.full((batch, 2, 4 * h, 4 * w), 0.3), generator=g).to(dev) for _ in range(seq_steps)]
+    gts = train_targets(xs, rank)
     n_red = 0
 
     def iteration():
@@ -437,7 +458,8 @@ def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
     del graphed, model, opt
     torch.cuda.empty_cache()
     return {'workload': 'BMCNet x4 training iteration (train.py:202-237): %d recurrent steps with BPTT, summed MSE, '
-                        'Adam(amsgrad), NFS LR %dx%d, batch %d per GPU, data-parallel' % (seq_steps, h, w, batch),
+                        'Adam(amsgrad, lr %g), NFS LR %dx%d, batch %d per GPU, data-parallel; targets = x4 bilinear base of the '
+                        'input counts + N(0, 0.05^2)' % (seq_steps, TRAIN_LR, h, w, batch),
             'weights': weights_desc, 'ms_per_iteration': ms, 'iterations_per_s': 1e3 / ms,
             'ms_per_iteration_eager': ms_eager, 'how': 'zero_grad + forward + backward replayed as one CUDA graph, then the '
             'all-reduce and the fused Adam launch (GraphedIteration); `ms_per_iteration_eager` = the same iteration issued '

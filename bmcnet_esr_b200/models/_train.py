@@ -730,7 +730,8 @@ class GraphedIteration:
     iteration keeps the parameters' AccumulateGrad nodes -- which remember the stream they were created on -- alive, and
     the capture then fails with "dependency created on uncaptured work in another stream"."""
 
-    def __init__(self, model, opt, xs, gts, group=None, warmup=2, capture_error_mode='thread_local', wgrad_stream=True):
+    def __init__(self, model, opt, xs, gts, group=None, warmup=2, capture_error_mode='thread_local', wgrad_stream=True,
+                 check_overflow=True):
         if not isinstance(opt, FusedAdamAMSGrad):
             raise _lib.BmcError('GraphedIteration needs FusedAdamAMSGrad (the gradients must live in one static buffer)')
         self.model, self.opt, self.group = model, opt, group
@@ -739,7 +740,15 @@ class GraphedIteration:
         self.xs = [x.to(dev).float().contiguous().clone() for x in xs]
         self.gts = [g.to(dev).float().contiguous().clone() for g in gts]
         self.loss = None
+        self.overflows = 0            # iterations whose gradients were not finite (step skipped, loss scale halved)
+        self.check_overflow = check_overflow
+        self._capture_args = (capture_error_mode, wgrad_stream)
         model.train()
+        self._capture(warmup)
+
+    def _capture(self, warmup):
+        model, dev = self.model, self.opt.flat.device
+        capture_error_mode, wgrad_stream = self._capture_args
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
@@ -789,5 +798,19 @@ class GraphedIteration:
         if self.group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
                                       and torch.distributed.get_world_size() > 1):
             allreduce_gradients(self.opt, self.group)
+        # The 16-bit activation gradients run under a static loss scale; a gradient spike (BPTT over the sequence does
+        # produce them: fp32 autograd on the same data shows max |grad| jump from 0.6 to 94 for one iteration) overflows
+        # them.  Like torch.amp's GradScaler: a non-finite gradient buffer skips the step and halves the scale -- which
+        # is a constant of the captured graph, so the iteration is re-captured.  After the all-reduce every rank sees the
+        # same buffer and takes the same decision.
+        if self.check_overflow and not bool(torch.isfinite(self.opt.grad).all()):
+            self.overflows += 1
+            if self.model.loss_scale > 1.0:
+                self.model.loss_scale = float(self.model.loss_scale) / 2.0
+                loss = self.loss.clone()
+                self.graph = None
+                self._capture(1)
+                return loss
+            return self.loss
         self.opt.step()
         return self.loss

@@ -26,6 +26,11 @@ torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
 
 
+def _lib_act():
+    from bmcnet_esr_b200 import _lib
+    return str(_lib.act_dtype()).replace('torch.', '')
+
+
 def _rel_max(a, b):
     return (a - b).abs().max().item() / max(b.abs().max().item(), 1e-30)
 
@@ -291,3 +296,35 @@ def test_graphed_iteration_side_stream_is_exact_and_reproducible(plain_ckpt):
         assert la == la2 == lc
         assert torch.equal(ga, ga2) and torch.equal(ga, gc)
     assert a[0][0] != a[1][0]
+
+
+def test_graphed_iteration_overflow_backoff(plain_ckpt):
+    """A loss scale far too large for fp16 (2^40) makes the very first gradient buffer non-finite: GraphedIteration must
+    skip the optimiser step (parameters unchanged, no NaN), halve the scale and re-capture until the gradients are finite,
+    then train normally."""
+    from bmcnet_esr_b200.models.BMCNet_plain import BMCNet_plain
+    from bmcnet_esr_b200.models._train import FusedAdamAMSGrad, GraphedIteration
+    if _lib_act() != 'float16':
+        pytest.skip('the loss scale only matters for fp16 activations')
+    b, h, w, steps = 2, 22, 40, 2
+    m = BMCNet_plain(4, 128, 5)
+    m.load_state_dict({k: v.clone() for k, v in plain_ckpt.items()}, strict=True)
+    m = m.cuda().train()
+    m.loss_scale = 2.0 ** 40
+    opt = FusedAdamAMSGrad(m.parameters())
+    xs = [synth_counts(b, h, w, 950 + s).cuda() for s in range(steps)]
+    g = torch.Generator().manual_seed(9)
+    gts = [torch.poisson(torch.full((b, 2, 4 * h, 4 * w), 0.3), generator=g).cuda() for _ in range(steps)]
+    before = opt.flat.clone()
+    it = GraphedIteration(m, opt, xs, gts, warmup=1)
+    it()
+    assert it.overflows == 1 and opt.step_count == 0 and m.loss_scale == 2.0 ** 39
+    assert torch.equal(opt.flat, before)                       # the step was skipped
+    for _ in range(40):
+        it()
+        if opt.step_count > 0:
+            break
+    assert opt.step_count == 1 and it.overflows >= 2 and m.loss_scale < 2.0 ** 39
+    assert torch.isfinite(opt.flat).all() and not torch.equal(opt.flat, before)
+    l1 = it().item()
+    assert np.isfinite(l1) and opt.step_count == 2
