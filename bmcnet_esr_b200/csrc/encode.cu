@@ -963,6 +963,34 @@ __global__ void __launch_bounds__(256) channels_windows_kernel(
     for (int k = threadIdx.x; k < nb; k += blockDim.x) o[k] = s[k];
 }
 
+// events_to_channels on ONE small window (the reference's call pattern: h5dataset.py:518-526 encodes every 1024-2048 event
+// window with its own call): zeroing, counting and the fp32 output in a single one-CTA launch instead of memset +
+// scatter + finalize.  Same arithmetic as channels_windows_kernel (fp32 shared-memory bins: sums of +1.0f below 2^24 are
+// exact integers in any order).
+constexpr long kOneCtaMaxEvents = 32768;
+__global__ void __launch_bounds__(1024) channels_one_kernel(float* xs, float* ys, const float* ps, long n, int H, int W,
+                                                            float* __restrict__ out, unsigned flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* s = reinterpret_cast<float*>(smem_raw);
+    const int nb = 2 * H * W;
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) s[k] = 0.f;
+    __syncthreads();
+    const bool quirks = !(flags & BMC_ENC_NO_QUIRKS), mut = flags & BMC_ENC_MUTATE;
+    for (long i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = xs[i], y = ys[i], p = ps[i];
+        Pix q = decode_xy(x, y, H, W, true);
+        const float w = p * p;
+        if (!q.oor) {
+            if (w != 0.f) atomicAdd(&s[(p < 0.f ? H * W : 0) + q.y * W + q.x], w);
+        } else {
+            if (quirks && p < 0.f) atomicAdd(&s[H * W + (H - 1) * W], w);
+            if (mut) { xs[i] = 0.f; ys[i] = 0.f; }
+        }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < nb; k += blockDim.x) out[k] = s[k];
+}
+
 // Window pipeline of the dataloader on raw recordings (h5dataset.py:197-210 compute_k_indices, :407-414
 // get_events, base_dataset.py:24-31 event_formatting, h5dataset.py:518-526 create_cnt_encoding): window i is
 // events [stride*i, min(stride*i + window, n_events - 1)) of the int16 / float64 arrays as stored in the
@@ -1201,6 +1229,14 @@ extern "C" BMC_EXPORT int bmc_encode_channels(float* xs, float* ys, const float*
     ChannelsOp op;
     op.xs = xs; op.ys = ys; op.ts = nullptr; op.ps = const_cast<float*>(ps);
     op.H = H; op.W = W; op.bins = 1; op.flags = flags | BMC_ENC_FLIP_Y;
+    if (n > 0 && n <= kOneCtaMaxEvents && (size_t)2 * H * W * 4 <= (size_t)kSmemBudget && !(flags & BMC_ENC_SPLIT_BINS)) {
+        const size_t smem = (size_t)2 * H * W * 4;             // one window: a single one-CTA launch
+        if (smem > 48 * 1024)
+            BMC_CUDA(cudaFuncSetAttribute(channels_one_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        channels_one_kernel<<<1, 1024, smem, as_stream(stream)>>>(xs, ys, ps, (long)n, H, W, out, flags);
+        BMC_CUDA(cudaGetLastError());
+        return BMC_OK;
+    }
     if (2L * H * W > kMaxBinsSmem16 && (H * W + 3) / 4 <= kRoleWords && (n >= kRoleMinEvents || (flags & BMC_ENC_SPLIT_BINS)) && n > 0 &&
         roles_enabled()) {
         CountsRole pol;                     // up to 360x640: one CTA per polarity over the same events, 8-bit counter planes
