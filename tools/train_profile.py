@@ -21,9 +21,9 @@ def main():
     m = BMCNet(4, 128, 5)
     m.load_state_dict(sd, strict=True)
     m = m.to(dev).train()
-    opt = FusedAdamAMSGrad(m.parameters())
+    opt = FusedAdamAMSGrad(m.parameters(), lr=bench.TRAIN_LR)
     xs = [synth_counts(b, h, w, 3000 + s).to(dev) for s in range(steps)]
-    gts = [torch.rand(b, 2, 4 * h, 4 * w, device=dev) for _ in range(steps)]
+    gts = bench.train_targets(xs, 0)
     it = GraphedIteration(m, opt, xs, gts, warmup=1)
     it(); it()
     torch.cuda.synchronize()
@@ -38,11 +38,14 @@ def main():
             c = rows.setdefault(n, [0, 0.0])
             c[0] += 1
             c[1] += e.device_time
-    tot = sum(v[1] for v in rows.values())
-    cnt = sum(v[0] for v in rows.values())
-    print('batch %d: %d kernels, %.1f ms of kernel time' % (b, cnt, tot / 1e3))
+    # (CUPTI may hand back the records of more than one replay: normalise by the Adam launches, one per iteration)
+    reps = max(1, sum(v[0] for k, v in rows.items() if 'adam_amsgrad' in k))
+    tot = sum(v[1] for v in rows.values()) / reps
+    cnt = sum(v[0] for v in rows.values()) // reps
+    print('overflows', it.overflows)
+    print('batch %d: %d kernels, %.1f ms of kernel time per iteration (%d iteration(s) in the trace)' % (b, cnt, tot / 1e3, reps))
     for n, (c, t) in sorted(rows.items(), key=lambda kv: -kv[1][1])[:45]:
-        print('%7d %9.1f us %5.1f%% %6.2f us/launch  %s' % (c, t, 100 * t / tot, t / c, n))
+        print('%7d %9.1f us %5.1f%% %6.2f us/launch  %s' % (c // reps, t / reps, 100 * t / reps / tot, t / c, n))
 
 
 if __name__ == '__main__':
