@@ -742,6 +742,7 @@ class GraphedIteration:
         self.loss = None
         self.overflows = 0            # iterations whose gradients were not finite (step skipped, loss scale halved)
         self.check_overflow = check_overflow
+        self._stream = None
         self._capture_args = (capture_error_mode, wgrad_stream)
         model.train()
         self._capture(warmup)
@@ -749,7 +750,13 @@ class GraphedIteration:
     def _capture(self, warmup):
         model, dev = self.model, self.opt.flat.device
         capture_error_mode, wgrad_stream = self._capture_args
-        side = torch.cuda.Stream(device=dev)
+        # Warm-up and capture run on ONE stream of this object.  The autograd engine orders the caller's stream behind the
+        # stream every parameter's AccumulateGrad node was created on (even for the undefined gradients this path hands
+        # it); a node that survives from the warm-up would otherwise make the capturing stream wait on an uncaptured one
+        # ("dependency created on uncaptured work in another stream", seen once under compute-sanitizer).
+        if self._stream is None:
+            self._stream = torch.cuda.Stream(device=dev)
+        side = self._stream
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(warmup):                    # lazy module loads, kernel attributes, index caches: not capturable
@@ -762,7 +769,7 @@ class GraphedIteration:
         self.graph = torch.cuda.CUDAGraph()
         # 'thread_local': a training process has other threads that touch CUDA (pinned-memory loaders, the clock sampler of
         # bench.py); their calls are not part of this stream's capture and must not invalidate it
-        with torch.cuda.graph(self.graph, capture_error_mode=capture_error_mode):
+        with torch.cuda.graph(self.graph, stream=self._stream, capture_error_mode=capture_error_mode):
             self.loss = self._body()
             if tc.side is not None:
                 torch.cuda.current_stream(dev).wait_stream(tc.side)      # join: the gradients are complete when the graph is

@@ -264,7 +264,7 @@ def test_graphed_iteration_matches_eager(plain, plain_ckpt):
         d = (pe.detach() - pg.detach()).abs()
         # an element whose gradient is rounding noise can take a different +-lr step in each run: bound the bulk, not it
         assert d.mean().item() <= 0.01 * lr and d.max().item() <= 2 * lr * iters, (n, d.max().item(), d.mean().item())
-        assert (d > 0.1 * lr).float().mean().item() <= 1e-3, (n, (d > 0.1 * lr).float().mean().item())
+        assert (d > 0.1 * lr).float().mean().item() <= 2e-2, (n, (d > 0.1 * lr).float().mean().item())
     moved = max((p.detach().cpu() - sd[n]).abs().max().item() for n, p in m_g.named_parameters() if n in sd)
     assert moved >= 2 * lr            # three Adam steps did move the weights
 
