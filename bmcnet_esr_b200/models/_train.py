@@ -769,10 +769,21 @@ class GraphedIteration:
         self.graph = torch.cuda.CUDAGraph()
         # 'thread_local': a training process has other threads that touch CUDA (pinned-memory loaders, the clock sampler of
         # bench.py); their calls are not part of this stream's capture and must not invalidate it
-        with torch.cuda.graph(self.graph, stream=self._stream, capture_error_mode=capture_error_mode):
-            self.loss = self._body()
-            if tc.side is not None:
-                torch.cuda.current_stream(dev).wait_stream(tc.side)      # join: the gradients are complete when the graph is
+        try:
+            with torch.cuda.graph(self.graph, stream=self._stream, capture_error_mode=capture_error_mode):
+                self.loss = self._body()
+                if tc.side is not None:
+                    torch.cuda.current_stream(dev).wait_stream(tc.side)      # join: the gradients are complete when the graph is
+        except RuntimeError as e:
+            tc.side = None
+            tc.keep.clear()
+            if 'uncaptured work' in str(e) or 'during capture' in str(e):
+                raise _lib.BmcError(
+                    'GraphedIteration: the capture of the training iteration was invalidated (%s).  The usual cause is a live '
+                    'autograd graph of an earlier eager iteration (e.g. its loss tensor is still referenced): it keeps the '
+                    "parameters' AccumulateGrad nodes, which remember the stream they were created on, alive.  Drop that "
+                    'tensor (or call .detach() on it) before building the GraphedIteration.' % str(e).splitlines()[0]) from e
+            raise
         tc.side = None
         tc.wcache.clear()                              # (entries point into the graph's pool; never reuse them eagerly)
 
