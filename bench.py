@@ -426,7 +426,7 @@ def run_train(cx, batch=2, seq_steps=8, h=45, w=80, iters=3, warm=1):
         if world > 1:
             n_red = allreduce_gradients(opt)
         opt.step()
-        return loss.detach()      # (a live autograd graph would keep the default stream's AccumulateGrad nodes alive)
+        return loss.detach()
 
     def timed(fn, n):
         if world > 1:

@@ -88,12 +88,24 @@ class _Ctx:
         self.ln_ws = None
         self.side = None          # GraphedIteration: the stream the weight-gradient kernels are recorded on
         self.keep = []            # gradient tensors the side stream reads (see _ConvFn.backward)
+        self._anchor = None
 
     def workspace(self, dev):
         nbytes = lib().bmc_conv_wgrad_workspace_bytes(WGRAD_SPLITS, 9, 128)
         if self.ws is None or self.ws.device != dev:
             self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         return self.ws
+
+    def new_anchor(self, dev):
+        """A fresh leaf that requires grad, one per forward call (see _ConvFn)."""
+        self._anchor = torch.zeros((), device=dev, requires_grad=True)
+        return self._anchor
+
+    @property
+    def anchor(self):
+        if self._anchor is None:            # building blocks used on their own (tests): any CUDA leaf will do
+            self.new_anchor(torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else 'cpu')
+        return self._anchor
 
     def ln_workspace(self, dev):
         if self.ln_ws is None or self.ln_ws.device != dev:
@@ -174,9 +186,12 @@ def _grad_buf(p):
 
 
 class _ConvFn(torch.autograd.Function):
-    """`weight` is passed as a tensor input only so that autograd sees the dependence on the parameters (the very
-    first convolutions of a sequence have no other input that requires grad); its gradient -- and the bias's --
-    is accumulated into `.grad` by the wgrad kernel, so backward returns None for it."""
+    """`weight` is a tensor input only so that the output requires grad (the very first convolutions of a sequence have
+    no other input that does): the caller passes the forward call's ANCHOR, a fresh 0-d leaf (`_Ctx.new_anchor`), not
+    the Parameter.  The parameter gradients -- weight and bias -- are accumulated into `.grad` by the wgrad kernel and
+    backward returns None for the anchor, so no Parameter ever enters the autograd graph and no AccumulateGrad node of a
+    Parameter (which remembers the stream it was created on, and outlives an iteration whenever a caller keeps a loss
+    tensor) can tie a captured iteration to another stream."""
 
     @staticmethod
     def forward(ctx, weight, tc, conv, segs, relu, use_bias, geom, *srcs):
@@ -249,9 +264,9 @@ def conv(tc, module, srcs, segs, geom, relu=False):
     `module.weight` it multiplies (-1 for padding channels).  bmc_conv_gemm takes up to 3 sources per job: a wider
     concatenation (conv_fs of BMCNet: 4) is the sum of two launches, bias in the first, ReLU after the sum."""
     if len(srcs) <= 3:
-        return _ConvFn.apply(module.weight, tc, module, segs, relu, True, geom, *srcs)
-    a = _ConvFn.apply(module.weight, tc, module, segs[:3], False, True, geom, *srcs[:3])
-    c = _ConvFn.apply(module.weight, tc, module, segs[3:], False, False, geom, *srcs[3:])
+        return _ConvFn.apply(tc.anchor, tc, module, segs, relu, True, geom, *srcs)
+    a = _ConvFn.apply(tc.anchor, tc, module, segs[:3], False, True, geom, *srcs[:3])
+    c = _ConvFn.apply(tc.anchor, tc, module, segs[3:], False, False, geom, *srcs[3:])
     out = a + c
     return F.relu(out) if relu else out
 
@@ -333,7 +348,7 @@ class _ConvStackFn(torch.autograd.Function):
 
 def conv_stack(tc, convs, srcs, segs, slabs, geom, relu=False):
     """convs[j](cat of the slabs slabs[s][j] of srcs[s]) for all j in one launch -> [J * rows, 128]."""
-    ws = [c.weight for c in convs]
+    ws = [tc.anchor]
     return _ConvStackFn.apply(tc, convs, segs, slabs, relu, geom, len(ws), *ws, *srcs)
 
 
@@ -448,7 +463,7 @@ class _AttendFn(torch.autograd.Function):
 
 
 def layernorm_rows(tc, norm, y):
-    return _LayerNormFn.apply(y, norm.weight, tc, norm)
+    return _LayerNormFn.apply(y, tc.anchor, tc, norm)
 
 
 def bie(tc, m, x1, x2, xs, geom):
@@ -505,6 +520,7 @@ def forward_plain(model, tc, x, x_h, x_o, init):
     sc, rp = model.scale, model.repeat
     k = sc * sc
     x = x.float()
+    tc.new_anchor(x.device)
     f2, x1p, x1n, x2p, x2n = _planes(x, rp)
     o = x_o.float() if init else F.pixel_unshuffle(x_o.float(), sc)
     o = _ScaleGrad.apply(o, 1.0 / tc.loss_scale)
@@ -545,6 +561,7 @@ def forward_full(model, tc, x, x_h, x_h_p, x_h_n, x_o, init):
     sc, rp = model.scale, model.repeat
     k = sc * sc
     x = x.float()
+    tc.new_anchor(x.device)
     f2, x1p, x1n, x2p, x2n = _planes(x, rp)
     o = x_o.float() if init else F.pixel_unshuffle(x_o.float(), sc)
     o = _ScaleGrad.apply(o, 1.0 / tc.loss_scale)
@@ -726,9 +743,9 @@ class GraphedIteration:
     `xs`: the sequence of model inputs [B,2,T,H,W] (any strides; `inp_cnt.transpose(1, 2)` in the reference), `gts`: the
     targets [B,2,kH',kW'].  The returned loss is a 0-d tensor that the next call overwrites.
 
-    Build it before any eager iteration, or after the last eager loss tensor is gone: a live autograd graph of an eager
-    iteration keeps the parameters' AccumulateGrad nodes -- which remember the stream they were created on -- alive, and
-    the capture then fails with "dependency created on uncaptured work in another stream"."""
+    No Parameter enters the autograd graph of this path (see _ConvFn: the gradient kernels write `.grad` themselves), so
+    the capture does not depend on what ran before it -- eager iterations on other streams, loss tensors still alive.
+    """
 
     def __init__(self, model, opt, xs, gts, group=None, warmup=2, capture_error_mode='thread_local', wgrad_stream=True,
                  check_overflow=True):
