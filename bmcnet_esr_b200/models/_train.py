@@ -796,10 +796,9 @@ class GraphedIteration:
             tc.keep.clear()
             if 'uncaptured work' in str(e) or 'during capture' in str(e):
                 raise _lib.BmcError(
-                    'GraphedIteration: the capture of the training iteration was invalidated (%s).  The usual cause is a live '
-                    'autograd graph of an earlier eager iteration (e.g. its loss tensor is still referenced): it keeps the '
-                    "parameters' AccumulateGrad nodes, which remember the stream they were created on, alive.  Drop that "
-                    'tensor (or call .detach() on it) before building the GraphedIteration.' % str(e).splitlines()[0]) from e
+                    'GraphedIteration: the capture of the training iteration was invalidated (%s): something inside the '
+                    'iteration touched a stream that is not part of the capture -- e.g. a custom loss / hook running on '
+                    'another stream, or tensors whose autograd history was recorded on another stream.' % str(e).splitlines()[0]) from e
             raise
         tc.side = None
         tc.wcache.clear()                              # (entries point into the graph's pool; never reuse them eagerly)
