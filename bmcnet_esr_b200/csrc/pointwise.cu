@@ -115,8 +115,9 @@ __global__ void pack_inputs(PackInputsParams p) {
     const uint32_t w1p = pack_act2(f1p, f1p), w2p = pack_act2(f2p, f2p);
     const uint32_t w1n = pack_act2(f1n, f1n), w2n = pack_act2(f2n, f2n);
     uint32_t* dw = reinterpret_cast<uint32_t*>(d);
-    dw[0] = w1p; dw[1] = pack_act2(f1p, f2p); dw[2] = w2p;
-    dw[3] = w1n; dw[4] = pack_act2(f1n, f2n); dw[5] = w2n;
+    // (rows are 128-byte aligned: the six words leave as one 16-byte and one 8-byte store)
+    *reinterpret_cast<uint4*>(dw) = make_uint4(w1p, pack_act2(f1p, f2p), w2p, w1n);
+    *reinterpret_cast<uint2*>(dw + 4) = make_uint2(pack_act2(f1n, f2n), w2n);
     if (!p.x_o && p.init) {                      // device-resident recurrence, reset: o = 0
 #pragma unroll
         for (int c = 6; c < 32; ++c) dw[c] = 0u;
@@ -168,15 +169,6 @@ __global__ void __launch_bounds__(128) emit_output(EmitParams p) {
     const int pix = (int)(idx - (long)b * HW);
     const int y = pix / g.W, x = pix - y * g.W;
     const long row = (long)b * g.R + (long)(y + 1) * g.Wp + (x + 1);
-    float o[32];
-    {
-        const float4* a4 = reinterpret_cast<const float4*>(p.a + row * 32);     // 128-byte aligned row
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float4 v = a4[i];
-            o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
-        }
-    }
     // the 4x4 outputs of an LR pixel interpolate inside its 3x3 neighbourhood of f2: 9 loads per plane;
     // tap indices / weights exactly as lerp_taps gives them (same arithmetic as one load per tap)
     int ky0[4], ky1[4], kx0[4], kx1[4];
@@ -188,8 +180,19 @@ __global__ void __launch_bounds__(128) emit_output(EmitParams p) {
         lerp_taps(4 * x + r, g.W, i0, i1, lx[r]); kx0[r] = i0 - (x - 1); kx1[r] = i1 - (x - 1);
     }
     const int yc[3] = {max(y - 1, 0), y, min(y + 1, g.H - 1)}, xc[3] = {max(x - 1, 0), x, min(x + 1, g.W - 1)};
-#pragma unroll
+    const int W4 = 4 * g.W;
+    // one output plane at a time (16 of the 32 values live: 128 -> 96 registers per thread)
+#pragma unroll 1
     for (int c = 0; c < 2; ++c) {
+        float o[16];
+        {
+            const float4* a4 = reinterpret_cast<const float4*>(p.a + row * 32 + c * 16);     // 64-byte aligned half row
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = a4[i];
+                o[4 * i] = v.x; o[4 * i + 1] = v.y; o[4 * i + 2] = v.z; o[4 * i + 3] = v.w;
+            }
+        }
         const float* f2 = p.x + b * p.xs[0] + c * p.xs[1] + p.xs[2];
         float P[3][3];
 #pragma unroll
@@ -208,22 +211,19 @@ __global__ void __launch_bounds__(128) emit_output(EmitParams p) {
             for (int rx = 0; rx < 4; ++rx) {
                 const float up = (1.f - ly[ry]) * sel3(ky0[ry], Hx[0][rx], Hx[1][rx], Hx[2][rx]) +
                                  ly[ry] * sel3(ky1[ry], Hx[0][rx], Hx[1][rx], Hx[2][rx]);
-                o[c * 16 + ry * 4 + rx] += up;
+                o[ry * 4 + rx] += up;
             }
-    }
-    if (p.out_o) {
-        const int W4 = 4 * g.W;
-#pragma unroll
-        for (int c = 0; c < 2; ++c)
+        if (p.out_o) {
 #pragma unroll
             for (int ry = 0; ry < 4; ++ry)
                 *reinterpret_cast<float4*>(p.out_o + ((long)b * 2 + c) * 16 * HW + (long)(4 * y + ry) * W4 + 4 * x) =
-                    make_float4(o[c * 16 + ry * 4], o[c * 16 + ry * 4 + 1], o[c * 16 + ry * 4 + 2], o[c * 16 + ry * 4 + 3]);
-    }
-    if (p.mi_next) {
-        uint2* d2 = reinterpret_cast<uint2*>(p.mi_next + row * 64 + 12);        // channels 12..43: byte offset 24, 8-byte aligned
+                    make_float4(o[ry * 4], o[ry * 4 + 1], o[ry * 4 + 2], o[ry * 4 + 3]);
+        }
+        if (p.mi_next) {
+            uint2* d2 = reinterpret_cast<uint2*>(p.mi_next + row * 64 + 12 + c * 16);   // channels 12 + 16 c ..: byte offset 24 + 32 c
 #pragma unroll
-        for (int c = 0; c < 8; ++c) d2[c] = make_uint2(pack_act2(o[4 * c], o[4 * c + 1]), pack_act2(o[4 * c + 2], o[4 * c + 3]));
+            for (int q = 0; q < 4; ++q) d2[q] = make_uint2(pack_act2(o[4 * q], o[4 * q + 1]), pack_act2(o[4 * q + 2], o[4 * q + 3]));
+        }
     }
 }
 
