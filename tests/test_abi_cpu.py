@@ -83,3 +83,17 @@ def test_initialisation_follows_reference_recipe():
     assert abs(w.std().item() - 0.1 * (2.0 / (128 * 9)) ** 0.5) < 2e-4
     assert float(m.neuro.conv_h.bias.abs().max()) == 0.0
     assert float(m.neuro.conv_fs.bias.abs().max()) > 0.0
+
+
+def test_training_launch_structure_threshold_and_bench_targets():
+    """Host logic of the training path that needs no GPU: stacked multi-job launches are used while one job fills at
+    most half a wave of SMs; the bench's synthetic targets have the prediction's shape and are seeded per rank."""
+    import torch
+    from bmcnet_esr_b200.models import _train as TR
+    import bench
+    assert TR._use_stack(2, 45, 80) and TR._use_stack(4, 45, 80) and not TR._use_stack(8, 45, 80)
+    assert TR._use_stack(16, 22, 40)
+    xs = [torch.rand(2, 2, 2, 6, 9) for _ in range(3)]
+    a, b2, c = bench.train_targets(xs, 0), bench.train_targets(xs, 0), bench.train_targets(xs, 1)
+    assert len(a) == 3 and a[0].shape == (2, 2, 24, 36)
+    assert all(torch.equal(u, v) for u, v in zip(a, b2)) and not torch.equal(a[0], c[0])

@@ -415,3 +415,25 @@ def test_cluster_bins_full_size(G):
     half = n // 2
     parts = sum(G.events_to_voxel(xs[s], ys[s], ts[s], ps[s], B, sensor_size=(h, w)) for s in (slice(0, half), slice(half, n)))
     assert float((full - parts).abs().max()) <= 1e-6 * max(1.0, float(full.abs().max())) * 4
+
+
+def test_cluster_bins_unaligned_views(G):
+    """The split-bins kernel on 4-byte-aligned views (scalar loads, single-event units) and on event counts that are not a
+    multiple of 4: same bits as the aligned call."""
+    n, dev = 700_001, 'cuda'
+    g = torch.Generator(device=dev).manual_seed(21)
+    ts = torch.sort(torch.rand(n + 1, device=dev, generator=g))[0]
+    ps = (torch.randint(0, 2, (n + 1,), device=dev, generator=g) * 2 - 1).float()
+    for (h, w), fn in (((180, 320), lambda x, y, t, p, hw: G.events_to_voxel(x, y, t, p, 5, sensor_size=hw)),
+                       ((360, 640), lambda x, y, t, p, hw: G.events_to_channels(x, y, p, sensor_size=hw))):
+        xs = torch.randint(-2, w + 2, (n + 1,), device=dev, generator=g).float()
+        ys = torch.randint(0, h, (n + 1,), device=dev, generator=g).float()
+        with _cluster_bins(G):
+            a = fn(xs[1:].clone(), ys[1:].clone(), ts[1:].clone(), ps[1:].clone(), (h, w))           # aligned copies
+            views = [t[1:] for t in (xs.clone(), ys.clone(), ts.clone(), ps.clone())]                   # storage offset 1
+            assert views[0].data_ptr() % 16 != 0
+            b = fn(*views, (h, w))
+        assert torch.equal(a, b)
+        with _cluster_bins(G, False):
+            c = fn(xs[1:].clone(), ys[1:].clone(), ts[1:].clone(), ps[1:].clone(), (h, w))           # default path
+        assert float((a - c).abs().max()) <= 1e-6 * max(1.0, float(c.abs().max())) * 4
