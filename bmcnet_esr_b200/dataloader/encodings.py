@@ -88,9 +88,8 @@ _WS = {}       # (device index, stream) -> scratch tensor, grown on demand
 def _workspace(dev, nbytes):
     """Scratch for one encoder call.  The library clears what it uses at the start of every call (on the call's
     stream), so one buffer per (device, stream) is reused instead of a fresh `torch.empty` per call; calls on the
-    same stream are ordered, calls on different streams get different buffers."""
-    with torch.cuda.device(dev):
-        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    same stream are ordered, calls on different streams get different buffers.  (Call with `dev` current.)"""
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
@@ -98,12 +97,25 @@ def _workspace(dev, nbytes):
     return ws
 
 
+_WS_BYTES = {}     # output elements -> bmc_encode_workspace_bytes
+
+
 def _run(fn, out, *args):
-    """Call an encoder entry with a scratch workspace sized for `out`."""
-    nbytes = lib().bmc_encode_workspace_bytes(out.numel())
-    ws = _workspace(out.device, nbytes)
-    with torch.cuda.device(out.device):
+    """Call an encoder entry with a scratch workspace sized for `out`.  The per-call host path matters for the
+    reference's call pattern (one call per 1024-2048 event window): no device-context switch when the tensors' device is
+    the current one, workspace size and buffer looked up, not queried."""
+    n = out.numel()
+    nbytes = _WS_BYTES.get(n)
+    if nbytes is None:
+        nbytes = _WS_BYTES[n] = lib().bmc_encode_workspace_bytes(n)
+    dev = out.device
+    if dev.index == torch.cuda.current_device():
+        ws = _workspace(dev, nbytes)
         check(fn(*args, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes))
+    else:
+        with torch.cuda.device(dev):
+            ws = _workspace(dev, nbytes)
+            check(fn(*args, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), nbytes))
     return out
 
 
@@ -231,7 +243,8 @@ def _stack_call(xs, ys, ps, ts_all, first, B, sensor_size, polarity):
         return torch.zeros([B, h, w], device=xs.device)
     out = torch.empty(*((2, B, h, w) if polarity else (B, h, w)), dtype=torch.float32, device=xs.device)
     nbytes = lib().bmc_encode_workspace_bytes(out.numel())
-    ws = _workspace(out.device, nbytes)
+    with torch.cuda.device(out.device):
+        ws = _workspace(out.device, nbytes)
 
     def launch(flags):
         with torch.cuda.device(out.device):
