@@ -163,7 +163,11 @@ __device__ __forceinline__ float sel3(int k, float a, float b, float c) { return
 __global__ void __launch_bounds__(128) emit_output(EmitParams p) {
     const Geom g = p.g;
     const int HW = g.H * g.W;
-    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    // one thread per (LR pixel, output plane c): 16 of the 32 values -- half the registers and twice the threads of a
+    // thread per pixel (128 -> 96 -> ~64 registers; the kernel is latency-bound on its loads)
+    const long tidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long idx = tidx >> 1;
+    const int c = (int)(tidx & 1);
     if (idx >= (long)g.B * HW) return;
     const int b = (int)(idx / HW);
     const int pix = (int)(idx - (long)b * HW);
@@ -181,9 +185,7 @@ __global__ void __launch_bounds__(128) emit_output(EmitParams p) {
     }
     const int yc[3] = {max(y - 1, 0), y, min(y + 1, g.H - 1)}, xc[3] = {max(x - 1, 0), x, min(x + 1, g.W - 1)};
     const int W4 = 4 * g.W;
-    // one output plane at a time (16 of the 32 values live: 128 -> 96 registers per thread)
-#pragma unroll 1
-    for (int c = 0; c < 2; ++c) {
+    {
         float o[16];
         {
             const float4* a4 = reinterpret_cast<const float4*>(p.a + row * 32 + c * 16);     // 64-byte aligned half row
@@ -307,7 +309,7 @@ int launch_pack_inputs(const PackInputsParams& p, cudaStream_t st) {
 }
 
 int launch_emit(const EmitParams& p, cudaStream_t st) {
-    const long total = (long)p.g.B * p.g.H * p.g.W;
+    const long total = 2L * p.g.B * p.g.H * p.g.W;          // (pixel, plane) pairs
     emit_output<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(p);
     BMC_CUDA(cudaGetLastError());
     return BMC_OK;
