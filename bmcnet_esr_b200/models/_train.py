@@ -325,11 +325,15 @@ class _ConvStackFn(torch.autograd.Function):
                 wgrads(dz)
             for t in (dz, *srcs):
                 t.record_stream(tc.side)
-        grads = []
+        # Data gradients, one multi-job launch per segment, routed back to the slabs the jobs read.  Cheap routes first:
+        # identity; a permutation of the slabs (one gather); every slab read by r consecutive jobs (one sum); else
+        # zeros + index_add.  A tensor passed for several segments (unclustering reads c for both) collects all of them in
+        # ONE buffer, returned for its first occurrence (None = zero for the others).
+        grads = [None] * len(srcs)
         ident = list(range(J))
+        first_of = {}
         for i, src in enumerate(srcs):
             if not ctx.needs_input_grad[7 + ctx.n_w + i]:
-                grads.append(None)
                 continue
             wt = _packed_stack(tc, convs, segs, 'bwd', i)
             g = K.conv_gemm_stack([dz], [ident], wt, None, J, b, h, w, taps)             # [J * rows, 128]
@@ -337,12 +341,30 @@ class _ConvStackFn(torch.autograd.Function):
             if c != 128:
                 g = g[:, :c]
             n_slabs = src.shape[0] // rows
-            if slabs[i] == list(range(n_slabs)):
-                grads.append(g.contiguous())
-            else:                                                                          # slabs read by several jobs add up
+            sl = list(slabs[i])
+            key = (src.data_ptr(), src.shape[0], c)
+            shared = sum(1 for k2, s2 in enumerate(srcs) if (s2.data_ptr(), s2.shape[0], s2.shape[1]) == key) > 1
+            if shared:
+                j0 = first_of.get(key)
+                if j0 is None:
+                    first_of[key] = i
+                    grads[i] = torch.zeros(n_slabs, rows, c, dtype=g.dtype, device=dev)
+                    j0 = i
+                grads[j0].index_add_(0, tc.cmap(sl, dev), g.reshape(J, rows, c))
+            elif sl == list(range(n_slabs)):
+                grads[i] = g.contiguous()
+            elif J == n_slabs and sorted(sl) == list(range(n_slabs)):                      # permutation: grad[sl[j]] = g[j]
+                inv = [0] * J
+                for j, t in enumerate(sl):
+                    inv[t] = j
+                grads[i] = g.reshape(J, rows, c).index_select(0, tc.lidx(inv, dev))
+            elif J % n_slabs == 0 and sl == [j // (J // n_slabs) for j in range(J)]:       # slab t read by jobs t r .. t r + r - 1
+                grads[i] = g.reshape(n_slabs, J // n_slabs, rows, c).sum(1)
+            else:
                 gs = torch.zeros(n_slabs, rows, c, dtype=g.dtype, device=dev)
-                gs.index_add_(0, tc.cmap(slabs[i], dev), g.reshape(J, rows, c))
-                grads.append(gs.view(n_slabs * rows, c))
+                gs.index_add_(0, tc.cmap(sl, dev), g.reshape(J, rows, c))
+                grads[i] = gs
+        grads = [None if g is None else g.reshape(-1, g.shape[-1]) for g in grads]
         return (None, None, None, None, None, None, None) + (None,) * ctx.n_w + tuple(grads)
 
 
@@ -583,20 +605,21 @@ def forward_full(model, tc, x, x_h, x_h_p, x_h_n, x_o, init):
     fs = lambda hx: conv(tc, nb.conv_fs, [xp_st, xn_st, hx, mo], [_R128, _seg(128), _seg(256), seg_o], geom, relu=True)
     xs, xs_p, xs_n = fs(hs), fs(hp), fs(hn)
     if _use_stack(b, h, w):
-        # ParallelBlk (BMCNet.py:19-32) on stacked operands: S = (xp_s, xn_s, xp_st, xn_st), PN = (xs_p, xs_n).  The four
+        # ParallelBlk (BMCNet.py:19-32) on stacked operands: S = (xp_s, xp_st, xn_s, xn_st), PN = (xs_p, xs_n).  The four
         # ResidualBlocks are one 4-job launch per convolution, lBIE on the positive and the negative triple shares every
         # launch (same weights, two instances), gBIE is one instance.
         rows = b * K.rows_per_image(h, w)
-        S = torch.cat([xp_s, xn_s, xp_st, xn_st], 0)
+        S = torch.cat([xp_s, xp_st, xn_s, xn_st], 0)          # (x1, x2) of the positive lBIE instance, then of the negative one
         PN = torch.cat([xs_p, xs_n], 0)
+        sl = lambda t, j: t[j * rows:(j + 1) * rows]
         for blk in nb.para_reschunk:
-            S = resblock_stack(tc, [blk.conv1, blk.conv2, blk.conv1_st, blk.conv2_st], S, geom)
-            X, PN = bie_stack(tc, blk.lBIE, _take(tc, S, [0, 2, 1, 3], rows), PN, 2, geom)     # (xp_s, xp_st, xn_s, xn_st)'
-            G, xs = bie_stack(tc, blk.gBIE, _take(tc, X, [0, 2], rows), xs, 1, geom)           # (xp_s, xn_s)''
-            S = torch.cat([G, _take(tc, X, [1, 3], rows)], 0)
+            S = resblock_stack(tc, [blk.conv1, blk.conv1_st, blk.conv2, blk.conv2_st], S, geom)
+            X, PN = bie_stack(tc, blk.lBIE, S, PN, 2, geom)                                      # (xp_s, xp_st, xn_s, xn_st)'
+            G, xs = bie_stack(tc, blk.gBIE, torch.cat([sl(X, 0), sl(X, 2)], 0), xs, 1, geom)     # (xp_s, xn_s)''
+            S = torch.cat([sl(G, 0), sl(X, 1), sl(G, 1), sl(X, 3)], 0)
         hsn = conv_stack(tc, [nb.conv_hs, nb.conv_hp, nb.conv_hn], [torch.cat([xs, PN], 0)], [_R128], [[0, 1, 2]], geom, relu=True)
         n_h, n_hp, n_hn = hsn[:rows], hsn[rows:2 * rows], hsn[2 * rows:]
-        a_o = conv(tc, nb.conv_o, [S[:rows], S[rows:2 * rows]], [_R128, _seg(128)], geom)
+        a_o = conv(tc, nb.conv_o, [sl(S, 0), sl(S, 2)], [_R128, _seg(128)], geom)
         pred = _reconstruct(_ScaleGrad.apply(a_o, tc.loss_scale), f2, geom, sc)
         return _state_out(n_h, geom, tc), _state_out(n_hp, geom, tc), _state_out(n_hn, geom, tc), pred
     for blk in nb.para_reschunk:
