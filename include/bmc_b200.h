@@ -65,7 +65,10 @@ const char* bmc_act_dtype(void);
                                     * the bins) whatever the event count; by default it is used from 2^24 events up (below
                                     * that the global-atomic path is as fast).  Same results. */
 
-/* Scratch bytes needed by any encoder call below for an output of `out_elems` floats. */
+/* Scratch bytes needed by any encoder call below for an output of `out_elems` floats: 8 bytes per output element (integer /
+ * fixed-point and fp32 partial grids), the stack encoders' bin boundaries, and a 512 KB list through which the split-bins
+ * kernel defers the in-place zeroing of out-of-range events (BMC_ENC_MUTATE).  Always query it: the size is part of the
+ * library build, not of the ABI. */
 size_t bmc_encode_workspace_bytes(int64_t out_elems);
 
 /* events_to_channels (encodings.py:290-305): per-polarity counts, out = device float[2][H][W].
